@@ -1,0 +1,107 @@
+"""ctypes binding of libmvk.so -- the ONLY compute path of this package.
+
+There is no CPU / eager fallback: if the CUDA library cannot be loaded (or no CUDA device is
+present when an op is called) the ops raise RuntimeError.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/mvk.h one to one.
+SIGNATURES = {
+    "mvk_error_string": (C.c_char_p, [i32]),
+    "mvk_last_cuda_error": (C.c_char_p, []),
+    "mvk_version": (i32, []),
+    "mvk_launch_count": (C.c_ulonglong, []),
+    "mvk_free_host": (None, [vp]),
+    "mvk_neighbors_workspace_bytes": (sz, [i32, i32, i32]),
+    "mvk_neighbors_count": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, vp, vp, vp]),
+    "mvk_neighbors_fill": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, vp]),
+    "mvk_neighbors_fill_i64": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, vp]),
+    "mvk_batch_neighbors_host": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, C.POINTER(vp), C.POINTER(i32)]),
+    "mvk_subsample_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "mvk_grid_subsample": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp, vp]),
+    "mvk_rotate_batch": (i32, [vp, i32, vp, i32, vp, i32, vp, vp]),
+    "mvk_grid_subsample_host": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, C.POINTER(vp),
+                                      C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(i32)]),
+    "mvk_kpconv_weighted": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, i32, f32, i32, i32, i32,
+                                  vp, vp, vp, vp]),
+    "mvk_kpconv_weighted_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, f32, i32, i32, vp,
+                                      i32, vp, vp]),
+    "mvk_split_bf16": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp]),
+    "mvk_gemm_bf16x3": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
+    "mvk_gemm_f32": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp, i32, i32, vp]),
+    "mvk_pool": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
+    "mvk_pool_bwd": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "mvk_unproject_views": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
+    "mvk_knn_workspace_bytes": (sz, [i32, i32]),
+    "mvk_knn_pixels": (i32, [vp, vp, i32, vp, i32, i32, vp, sz, vp, vp]),
+    "mvk_group_points": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "mvk_group_points_bwd": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp]),
+    "mvk_fa_layer": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
+    "mvk_fa_gather": (i32, [vp, i64, i64, i32, vp, vp, i32, i32, vp, vp, i32, vp]),
+    "mvk_fa_reduce": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp]),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def lib():
+    """Load (building first if stale and nvcc is present).  Raises if the CUDA library is unavailable."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB
+        if not _build.is_current():
+            if _build.nvcc_path() is not None:
+                path = _build.build()
+            elif not os.path.exists(path):
+                raise RuntimeError(
+                    "libmvk.so not found and nvcc unavailable: the CUDA extension is required "
+                    "(there is no CPU fallback). Run `python -c 'import __graft_entry__ as g; g.build()'`.")
+        handle = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError = header/library mismatch: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = handle
+    return _LIB
+
+
+class MvkError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        l = lib()
+        msg = l.mvk_error_string(rc).decode()
+        if rc == -3:
+            msg += ": " + l.mvk_last_cuda_error().decode()
+        raise MvkError(msg)
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("mvkpconv_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    lib()
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a (contiguous) torch tensor, or NULL."""
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_contiguous(), "libmvk expects contiguous tensors"
+    return C.c_void_p(t.data_ptr())

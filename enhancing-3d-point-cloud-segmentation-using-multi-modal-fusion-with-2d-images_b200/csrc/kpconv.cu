@@ -1,0 +1,475 @@
+// KPConv stage A: neighbour-feature gather + kernel-point influence (forward and backward),
+// the bf16 hi/lo splitter feeding the tensor-core contraction, and the gather pools.
+// Reference semantics: KPConv-PyTorch/models/blocks.py:277-363 (stage A), :79-110 (pools).
+//
+// One warp owns one query point.
+//   phase 1  lanes = neighbours: relative position, the K kernel-point distances and influences.
+//            The influence matrix w[h][k] is SPARSE (a neighbour lies within KP_extent of ~2 of the
+//            15 kernel points), so non-zero entries are ballot-compacted into per-kernel-point lists
+//            {support row, weight} in shared memory (deterministic order: by neighbour slot).
+//   phase 2  lanes = channels: for every kernel point walk its list, gather the support feature
+//            rows with coalesced vector loads (x is L2-resident at these sizes) and accumulate in
+//            registers; rows of the weighted matrix [nq, K*cin] are written once, coalesced.
+// Shadow neighbours (index >= ns) contribute exactly zero in the reference (zero feature row) and
+// are skipped.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace mvk {
+namespace {
+
+constexpr int KP_MAX = 32;
+
+struct KpArgs {
+    const float* q;
+    const float* s;
+    const void* inds;
+    const float* x;
+    const float* kp;
+    int nq, ns, h, cin, K, ld;
+    float extent;
+    int influence, aggregation;
+};
+
+template <typename IdxT>
+__device__ __forceinline__ int load_idx(const void* inds, size_t off) {
+    return (int)((const IdxT*)inds)[off];
+}
+
+// Influence of kernel point at squared distance d2 (blocks.py:329-346).
+__device__ __forceinline__ float influence_w(float d2, float extent, int mode) {
+    if (mode == 1) {
+        // zero beyond the extent: skip the IEEE sqrt/div there (guard band keeps boundary cases exact)
+        if (d2 > extent * extent * 1.0001f) return 0.f;
+        return fmaxf(0.f, 1.f - __fdiv_rn(__fsqrt_rn(d2), extent));
+    }
+    if (mode == 0) return 1.f;
+    float sigma = extent * 0.3f;
+    return __expf(-d2 / (2.f * sigma * sigma + 1e-9f));
+}
+
+// Phase 1 shared by forward and backward: fills per-kernel-point lists.
+//   jl/wl : [K][hcap]   cnt : [K]
+template <typename IdxT>
+__device__ __forceinline__ void build_lists(const KpArgs& a, int i, int lane, const float* s_kp,
+                                            int* jl, float* wl, int* cnt, int hcap) {
+    for (int k = lane; k < a.K; k += 32) cnt[k] = 0;
+    __syncwarp();
+    const float qx = a.q[3 * i], qy = a.q[3 * i + 1], qz = a.q[3 * i + 2];
+    for (int h0 = 0; h0 < a.h; h0 += 32) {
+        int h = h0 + lane;
+        int j = a.ns;
+        if (h < a.h) j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
+        bool real = (j >= 0 && j < a.ns);
+        float rx = 0.f, ry = 0.f, rz = 0.f;
+        if (real) {
+            rx = a.s[3 * j] - qx;
+            ry = a.s[3 * j + 1] - qy;
+            rz = a.s[3 * j + 2] - qz;
+        }
+        int kmin = 0;
+        if (a.aggregation == 1) {  // 'closest': only the nearest kernel point keeps its influence
+            float best = 3.4e38f;
+            for (int k = 0; k < a.K; k++) {
+                float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+                float d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 < best) {
+                    best = d2;
+                    kmin = k;
+                }
+            }
+        }
+        for (int k = 0; k < a.K; k++) {
+            float dx = rx - s_kp[3 * k], dy = ry - s_kp[3 * k + 1], dz = rz - s_kp[3 * k + 2];
+            float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            float w = influence_w(d2, a.extent, a.influence);
+            if (a.aggregation == 1 && k != kmin) w = 0.f;
+            bool nz = real && (w > 0.f);
+            int base = cnt[k];
+            unsigned int m = __ballot_sync(0xffffffffu, nz);
+            if (nz) {
+                int pos = base + __popc(m & ((1u << lane) - 1));
+                jl[k * hcap + pos] = j;
+                wl[k * hcap + pos] = w;
+            }
+            if (lane == 0) cnt[k] = base + __popc(m);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ void store_out(float* of, __nv_bfloat16* ohi, __nv_bfloat16* olo,
+                                          size_t off, float v) {
+    if (of) of[off] = v;
+    if (ohi) {
+        __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        ohi[off] = hi;
+        olo[off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+template <typename IdxT, int V>
+__global__ void __launch_bounds__(256)
+kp_weighted_fwd(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                __nv_bfloat16* __restrict__ out_lo, int hcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* s_kp = (float*)smem_raw;  // [KP_MAX*3]
+    size_t per_warp = (size_t)a.K * hcap * 8 + KP_MAX * 4;
+    unsigned char* wbase = smem_raw + KP_MAX * 3 * 4 + wib * per_warp;
+    int* jl = (int*)wbase;
+    float* wl = (float*)(wbase + (size_t)a.K * hcap * 4);
+    int* cnt = (int*)(wbase + (size_t)a.K * hcap * 8);
+    for (int t = threadIdx.x; t < a.K * 3; t += blockDim.x) s_kp[t] = a.kp[t];
+    __syncthreads();
+    const int kd = a.K * a.cin;
+
+    for (int i = blockIdx.x * wpb + wib; i < a.nq; i += gridDim.x * wpb) {
+        build_lists<IdxT>(a, i, lane, s_kp, jl, wl, cnt, hcap);
+        const size_t row = (size_t)i * a.ld;
+        for (int cb = 0; cb < a.cin; cb += 32 * V) {
+            const int c = cb + lane * V;
+            const bool cok = c < a.cin;  // cin % V == 0 guaranteed by the launcher
+            for (int k = 0; k < a.K; k++) {
+                float acc[V];
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[v] = 0.f;
+                const int n = cnt[k];
+                const int* jk = jl + k * hcap;
+                const float* wk = wl + k * hcap;
+                if (cok) {
+                    int t = 0;
+                    for (; t + 4 <= n; t += 4) {
+                        float xv[4][V];
+                        float w4[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const float* xp = a.x + (size_t)jk[t + u] * a.cin + c;
+                            w4[u] = wk[t + u];
+                            if (V == 4) {
+                                float4 t4 = __ldg((const float4*)xp);
+                                xv[u][0] = t4.x; xv[u][1 % V] = t4.y; xv[u][2 % V] = t4.z; xv[u][3 % V] = t4.w;
+                            } else if (V == 2) {
+                                float2 t2 = __ldg((const float2*)xp);
+                                xv[u][0] = t2.x; xv[u][1 % V] = t2.y;
+                            } else {
+                                xv[u][0] = __ldg(xp);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+#pragma unroll
+                            for (int v = 0; v < V; v++) acc[v] = fmaf(w4[u], xv[u][v], acc[v]);
+                    }
+                    for (; t < n; t++) {
+                        const float* xp = a.x + (size_t)jk[t] * a.cin + c;
+                        float w = wk[t];
+#pragma unroll
+                        for (int v = 0; v < V; v++) acc[v] = fmaf(w, __ldg(xp + v), acc[v]);
+                    }
+                    const size_t off = row + (size_t)k * a.cin + c;
+                    if (out_f32) {
+                        if (V == 4) *(float4*)(out_f32 + off) = make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]);
+                        else if (V == 2) *(float2*)(out_f32 + off) = make_float2(acc[0], acc[1 % V]);
+                        else out_f32[off] = acc[0];
+                    }
+                    if (out_hi) {
+                        __nv_bfloat16 hi[V], lo[V];
+#pragma unroll
+                        for (int v = 0; v < V; v++) {
+                            hi[v] = __float2bfloat16_rn(acc[v]);
+                            lo[v] = __float2bfloat16_rn(acc[v] - __bfloat162float(hi[v]));
+                        }
+                        if (V == 4) {
+                            *(uint2*)(out_hi + off) = *(uint2*)hi;
+                            *(uint2*)(out_lo + off) = *(uint2*)lo;
+                        } else if (V == 2) {
+                            *(unsigned int*)(out_hi + off) = *(unsigned int*)hi;
+                            *(unsigned int*)(out_lo + off) = *(unsigned int*)lo;
+                        } else {
+                            out_hi[off] = hi[0];
+                            out_lo[off] = lo[0];
+                        }
+                    }
+                }
+            }
+        }
+        for (int c = kd + lane; c < a.ld; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
+        __syncwarp();
+    }
+}
+
+// grad_x[j, c] += sum_k w_ihk * gw[i, k*cin + c].  Per neighbour: one vector atomic per channel group.
+template <typename IdxT, int V>
+__global__ void __launch_bounds__(256)
+kp_weighted_bwd(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx, int hcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float* s_kp = (float*)smem_raw;
+    // per warp: lists (K*hcap*8 + KP_MAX*4) + gradient tile [K][32*V] floats
+    size_t per_warp = (size_t)a.K * hcap * 8 + KP_MAX * 4 + (size_t)a.K * 32 * V * 4;
+    unsigned char* wbase = smem_raw + KP_MAX * 3 * 4 + wib * per_warp;
+    int* jl = (int*)wbase;
+    float* wl = (float*)(wbase + (size_t)a.K * hcap * 4);
+    int* cnt = (int*)(wbase + (size_t)a.K * hcap * 8);
+    float* gt = (float*)(wbase + (size_t)a.K * hcap * 8 + KP_MAX * 4);
+    for (int t = threadIdx.x; t < a.K * 3; t += blockDim.x) s_kp[t] = a.kp[t];
+    __syncthreads();
+
+    for (int i = blockIdx.x * wpb + wib; i < a.nq; i += gridDim.x * wpb) {
+        build_lists<IdxT>(a, i, lane, s_kp, jl, wl, cnt, hcap);
+        const size_t row = (size_t)i * a.ld;
+        for (int cb = 0; cb < a.cin; cb += 32 * V) {
+            const int c = cb + lane * V;
+            const bool cok = c < a.cin;
+            // this lane's gradient columns for every kernel point (own column: no sync needed)
+            for (int k = 0; k < a.K; k++) {
+#pragma unroll
+                for (int v = 0; v < V; v++)
+                    gt[(k * 32 + lane) * V + v] = cok ? gw[row + (size_t)k * a.cin + c + v] : 0.f;
+            }
+            // Walk neighbours in slot order; a neighbour appears in list k at a monotonically
+            // increasing cursor (lists are ordered by slot), so keep one cursor per kernel point.
+            // Cursors live in registers of lane k (K <= 32) and are broadcast by shuffle.
+            int cursor = 0;
+            for (int h = 0; h < a.h; h++) {
+                int j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
+                if (j < 0 || j >= a.ns) continue;  // warp-uniform
+                // which kernel points list this neighbour next?
+                bool mine = false;
+                if (lane < a.K && cursor < cnt[lane]) mine = (jl[lane * hcap + cursor] == j);
+                unsigned int m = __ballot_sync(0xffffffffu, mine);
+                if (m == 0) continue;
+                float acc[V];
+#pragma unroll
+                for (int v = 0; v < V; v++) acc[v] = 0.f;
+                unsigned int mm = m;
+                while (mm) {
+                    int k = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    int cur = __shfl_sync(0xffffffffu, cursor, k);
+                    float w = wl[k * hcap + cur];
+#pragma unroll
+                    for (int v = 0; v < V; v++) acc[v] = fmaf(w, gt[(k * 32 + lane) * V + v], acc[v]);
+                }
+                if (mine) cursor++;
+                if (cok) {
+                    float* dst = gx + (size_t)j * a.cin + c;
+                    if (V == 4) atomicAdd((float4*)dst, make_float4(acc[0], acc[1 % V], acc[2 % V], acc[3 % V]));
+                    else if (V == 2) atomicAdd((float2*)dst, make_float2(acc[0], acc[1 % V]));
+                    else atomicAdd(dst, acc[0]);
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+split_bf16_kernel(const float* __restrict__ src, int rows, int cols, int src_ld,
+                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows_pad, int ld) {
+    size_t total = (size_t)rows_pad * ld;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(t / ld), c = (int)(t % ld);
+        float v = (r < rows && c < cols) ? src[(size_t)r * src_ld + c] : 0.f;
+        __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[t] = h;
+        if (lo) lo[t] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// mode 0: max over neighbours with a ZERO shadow row (blocks.py:93-110); mode 1: first column.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pool_fwd(const float* __restrict__ x, int ns, int c, const void* __restrict__ inds, int nq, int h,
+         int mode, float* __restrict__ out, int* __restrict__ arg) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nq; i += gridDim.x * wpb) {
+        for (int ch = lane; ch < c; ch += 32) {
+            if (mode == 1) {
+                int j = load_idx<IdxT>(inds, (size_t)i * h);
+                out[(size_t)i * c + ch] = (j >= 0 && j < ns) ? x[(size_t)j * c + ch] : 0.f;
+            } else {
+                float best = 0.f;
+                int bj = ns;
+                bool first = true;
+                for (int t = 0; t < h; t++) {
+                    int j = load_idx<IdxT>(inds, (size_t)i * h + t);
+                    bool real = j >= 0 && j < ns;
+                    float v = real ? x[(size_t)j * c + ch] : 0.f;
+                    if (first || v > best) {
+                        best = v;
+                        bj = real ? j : ns;
+                        first = false;
+                    }
+                }
+                out[(size_t)i * c + ch] = best;
+                if (arg) arg[(size_t)i * c + ch] = bj;
+            }
+        }
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pool_bwd(const float* __restrict__ go, int nq, int c, const int* __restrict__ arg,
+         const void* __restrict__ inds, int h, int mode, int ns, float* __restrict__ gx) {
+    size_t total = (size_t)nq * c;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        int i = (int)(t / c), ch = (int)(t % c);
+        int j = mode == 1 ? load_idx<IdxT>(inds, (size_t)i * h) : arg[t];
+        if (j >= 0 && j < ns) atomicAdd(&gx[(size_t)j * c + ch], go[t]);
+    }
+}
+
+int pick_v(int cin) { return (cin % 128 == 0) ? 4 : ((cin % 64 == 0) ? 2 : 1); }
+
+}  // namespace
+}  // namespace mvk
+
+using namespace mvk;
+
+extern "C" {
+
+int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                        int idx_is_i64, int h, const float* x, int cin, const float* kernel_points,
+                        int num_kp, float kp_extent, int influence, int aggregation, int ld,
+                        float* out_f32, void* out_hi, void* out_lo, mvk_stream_t stream) {
+    if (nq < 0 || ns < 0 || h < 1 || cin < 1 || num_kp < 1 || num_kp > KP_MAX || ld < num_kp * cin ||
+        (!out_f32 && !(out_hi && out_lo)) || !(kp_extent > 0.f))
+        return MVK_ERR_INVALID_ARG;
+    if (influence < 0 || influence > 2 || aggregation < 0 || aggregation > 1) return MVK_ERR_UNSUPPORTED;
+    if (nq == 0) return MVK_OK;
+    KpArgs a{q_pts, s_pts, neighb_inds, x, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
+             influence, aggregation};
+    int hcap = (h + 31) / 32 * 32;
+    size_t per_warp = (size_t)num_kp * hcap * 8 + KP_MAX * 4;
+    if (per_warp + 512 > 200 * 1024) return MVK_ERR_RANGE;
+    int wpb = (int)((96 * 1024) / per_warp);
+    wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
+    size_t smem = KP_MAX * 3 * 4 + per_warp * wpb;
+    int blocks = (nq + wpb - 1) / wpb;
+    int maxb = num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    cudaStream_t st = (cudaStream_t)stream;
+    int V = pick_v(cin);
+    // vector stores need 16B/8B aligned rows
+    if (V == 4 && (ld % 4 != 0)) V = 1;
+    if (V == 2 && (ld % 2 != 0)) V = 1;
+#define LAUNCH_FWD(IDX, VV)                                                                          \
+    do {                                                                                             \
+        auto kern = kp_weighted_fwd<IDX, VV>;                                                        \
+        MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<blocks, wpb * 32, smem, st>>>(a, out_f32, (__nv_bfloat16*)out_hi,                     \
+                                             (__nv_bfloat16*)out_lo, hcap);                          \
+    } while (0)
+    if (idx_is_i64) {
+        if (V == 4) LAUNCH_FWD(long long, 4);
+        else if (V == 2) LAUNCH_FWD(long long, 2);
+        else LAUNCH_FWD(long long, 1);
+    } else {
+        if (V == 4) LAUNCH_FWD(int, 4);
+        else if (V == 2) LAUNCH_FWD(int, 2);
+        else LAUNCH_FWD(int, 1);
+    }
+#undef LAUNCH_FWD
+    MVK_LAUNCHED("kp_weighted_fwd");
+    return MVK_OK;
+}
+
+int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int ns,
+                            const void* neighb_inds, int idx_is_i64, int h, int cin,
+                            const float* kernel_points, int num_kp, float kp_extent, int influence,
+                            int aggregation, const float* grad_weighted, int ld, float* grad_x,
+                            mvk_stream_t stream) {
+    if (nq < 0 || ns < 0 || h < 1 || cin < 1 || num_kp < 1 || num_kp > KP_MAX || ld < num_kp * cin ||
+        !grad_weighted || !grad_x || !(kp_extent > 0.f))
+        return MVK_ERR_INVALID_ARG;
+    if (influence < 0 || influence > 2 || aggregation < 0 || aggregation > 1) return MVK_ERR_UNSUPPORTED;
+    if (nq == 0) return MVK_OK;
+    KpArgs a{q_pts, s_pts, neighb_inds, nullptr, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
+             influence, aggregation};
+    int V = pick_v(cin);
+    int hcap = (h + 31) / 32 * 32;
+    size_t per_warp = (size_t)num_kp * hcap * 8 + KP_MAX * 4 + (size_t)num_kp * 32 * V * 4;
+    if (per_warp + 512 > 200 * 1024) return MVK_ERR_RANGE;
+    int wpb = (int)((96 * 1024) / per_warp);
+    wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
+    size_t smem = KP_MAX * 3 * 4 + per_warp * wpb;
+    int blocks = (nq + wpb - 1) / wpb;
+    int maxb = num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_BWD(IDX, VV)                                                                          \
+    do {                                                                                             \
+        auto kern = kp_weighted_bwd<IDX, VV>;                                                        \
+        MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<blocks, wpb * 32, smem, st>>>(a, grad_weighted, grad_x, hcap);                        \
+    } while (0)
+    if (idx_is_i64) {
+        if (V == 4) LAUNCH_BWD(long long, 4);
+        else if (V == 2) LAUNCH_BWD(long long, 2);
+        else LAUNCH_BWD(long long, 1);
+    } else {
+        if (V == 4) LAUNCH_BWD(int, 4);
+        else if (V == 2) LAUNCH_BWD(int, 2);
+        else LAUNCH_BWD(int, 1);
+    }
+#undef LAUNCH_BWD
+    MVK_LAUNCHED("kp_weighted_bwd");
+    return MVK_OK;
+}
+
+int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, void* lo, int rows_pad,
+                   int ld, mvk_stream_t stream) {
+    if (!src || !hi || rows < 0 || cols < 0 || rows_pad < rows || ld < cols || src_ld < cols)
+        return MVK_ERR_INVALID_ARG;
+    size_t total = (size_t)rows_pad * ld;
+    if (total == 0) return MVK_OK;
+    int blocks = (int)((total + 255) / 256);
+    int maxb = num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, src_ld,
+                                                                (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                rows_pad, ld);
+    MVK_LAUNCHED("split_bf16");
+    return MVK_OK;
+}
+
+int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, int nq, int h, int mode,
+             float* out, int* arg_out, mvk_stream_t stream) {
+    if (!x || !inds || !out || c < 1 || h < 1 || nq < 0 || mode < 0 || mode > 1) return MVK_ERR_INVALID_ARG;
+    if (nq == 0) return MVK_OK;
+    int blocks = (nq + 7) / 8;
+    int maxb = num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (idx_is_i64)
+        pool_fwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+    else
+        pool_fwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+    MVK_LAUNCHED("pool_fwd");
+    return MVK_OK;
+}
+
+int mvk_pool_bwd(const float* grad_out, int nq, int c, const int* arg, const void* inds,
+                 int idx_is_i64, int h, int mode, int ns, float* grad_x, mvk_stream_t stream) {
+    if (!grad_out || !grad_x || c < 1 || nq < 0 || (mode == 0 && !arg) || (mode == 1 && !inds))
+        return MVK_ERR_INVALID_ARG;
+    if (nq == 0) return MVK_OK;
+    size_t total = (size_t)nq * c;
+    int blocks = (int)((total + 255) / 256);
+    int maxb = num_sms() * 16;
+    if (blocks > maxb) blocks = maxb;
+    if (idx_is_i64)
+        pool_bwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, nq, c, arg, inds, h, mode, ns, grad_x);
+    else
+        pool_bwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, nq, c, arg, inds, h, mode, ns, grad_x);
+    MVK_LAUNCHED("pool_bwd");
+    return MVK_OK;
+}
+
+}  // extern "C"

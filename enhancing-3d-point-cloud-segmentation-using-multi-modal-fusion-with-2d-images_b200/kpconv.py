@@ -1,0 +1,301 @@
+"""KPConv (rigid) as a drop-in ``nn.Module`` backed by libmvk's hand-written sm_100a kernels.
+
+Mirror of the reference operator (KPConv-PyTorch/models/blocks.py:143-379): same constructor
+signature, same ``forward(q_pts, s_pts, neighb_inds, x)``, same parameter names / shapes
+(``weights`` [K, Cin, Cout], ``kernel_points`` [K, 3] with requires_grad=False) so reference
+checkpoints load, same ``__repr__``.
+
+forward  =  stage A  mvk_kpconv_weighted  (neighbour gather + kernel-point influence -> [N, K*Cin])
+          + stage B  contraction with W [K*Cin, Cout]:
+                "bf16x3" (default)  tcgen05/TMA tensor cores, hi/lo split bf16, fp32 accumulate
+                "bf16"              tcgen05/TMA tensor cores, plain bf16 operands (stated separately)
+                "fp32"              strict fp32 FFMA contraction
+backward =  dA = dOut W^T (same contraction kernel),  dW = A^T dOut (split-K, fp32 atomics),
+            dX = scatter of dA through the influences (mvk_kpconv_weighted_bwd, fp32 atomics).
+
+Unsupported reference modes raise instead of silently falling back: deformable / modulated
+KPConv (blocks.py:243-325) is phase 2.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+from torch.nn.init import kaiming_uniform_
+from torch.nn.parameter import Parameter
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .kernel_points import load_kernels
+
+_INFLUENCE = {"constant": 0, "linear": 1, "gaussian": 2}
+_AGGREGATION = {"sum": 0, "closest": 1}
+CONTRACTIONS = ("bf16x3", "bf16", "fp32")
+
+DEFAULT_CONTRACTION = os.environ.get("MVK_CONTRACTION", "bf16x3")
+
+
+def _round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def _idx(t):
+    if t.dtype not in (torch.int64, torch.int32):
+        raise RuntimeError("neighb_inds must be int64 (reference dtype) or int32")
+    return t.contiguous(), (1 if t.dtype == torch.int64 else 0)
+
+
+def _split_k_for(m_tiles, n_tiles, kb_total):
+    target = 2 * 148
+    return max(1, min(kb_total, target // max(1, m_tiles * n_tiles)))
+
+
+class _KPConvFunction(torch.autograd.Function):
+    """out[i] = sum_k (sum_h w_ihk x[j_ih]) @ W[k]   (blocks.py:277-374, rigid)."""
+
+    @staticmethod
+    def forward(ctx, q_pts, s_pts, neighb_inds, x, weights, kernel_points, kp_extent, influence,
+                aggregation, contraction):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if not x.is_cuda:
+            raise RuntimeError("KPConv: tensors must live on a CUDA device (no CPU fallback)")
+        q = q_pts.detach().contiguous().float()
+        s = s_pts.detach().contiguous().float()
+        inds, is64 = _idx(neighb_inds)
+        xf = x.detach().contiguous().float()
+        w = weights.detach().contiguous().float()
+        kp = kernel_points.detach().contiguous().float()
+        nq, ns, h = q.shape[0], s.shape[0], inds.shape[1]
+        K, cin, cout = w.shape
+        kd = K * cin
+        dev = xf.device
+        out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
+        st = stream_ptr()
+        with torch.cuda.device(dev):
+            if contraction == "fp32":
+                ld = kd
+                A = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                check(L.mvk_kpconv_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin,
+                                            ptr(kp), K, float(kp_extent), influence, aggregation, ld,
+                                            ptr(A), None, None, st))
+                if nq > 0:
+                    check(L.mvk_gemm_f32(ptr(A), ld, 1, ptr(w), cout, 1, nq, cout, kd, ptr(out), cout, 1, st))
+                saved = (A,)
+            else:
+                terms = 3 if contraction == "bf16x3" else 1
+                ld = _round_up(kd, 64)
+                npad = _round_up(cout, 64)
+                a_hi = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
+                a_lo = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
+                check(L.mvk_kpconv_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin,
+                                            ptr(kp), K, float(kp_extent), influence, aggregation, ld,
+                                            None, ptr(a_hi), ptr(a_lo), st))
+                w_hi = torch.empty((ld, npad), dtype=torch.bfloat16, device=dev)
+                w_lo = torch.empty((ld, npad), dtype=torch.bfloat16, device=dev)
+                check(L.mvk_split_bf16(ptr(w), kd, cout, cout, ptr(w_hi), ptr(w_lo), ld, npad, st))
+                if nq > 0:
+                    check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, ld, ptr(w_hi), ptr(w_lo), 1, npad,
+                                            nq, npad, ld, ptr(out), cout, cout, terms, 1, st))
+                saved = (a_hi, a_lo, w_hi, w_lo)
+        ctx.save_for_backward(q, s, inds, kp, w, *saved)
+        ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = _lib.lib()
+        q, s, inds, kp, w, *saved = ctx.saved_tensors
+        nq, ns, h, K, cin, cout, extent, influence, aggregation, contraction, is64 = ctx.cfg
+        kd = K * cin
+        dev = grad_out.device
+        go = grad_out.detach().contiguous().float()
+        need_x, need_w = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        gx = gw = None
+        st = stream_ptr()
+        with torch.cuda.device(dev):
+            if contraction == "fp32":
+                (A,) = saved
+                ld = kd
+                if need_w:
+                    gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
+                    if nq > 0:
+                        split = max(1, min(nq // 64, 2 * 148 // max(1, ((kd + 63) // 64) * ((cout + 63) // 64))))
+                        # dW[kd, cout] = A^T dOut : A'(m, k) = A[k*ld + m]
+                        check(L.mvk_gemm_f32(ptr(A), 1, ld, ptr(go), cout, 1, kd, cout, nq, ptr(gw), cout,
+                                             split, st))
+                if need_x:
+                    dA = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                    if nq > 0:
+                        # dA[nq, kd] = dOut W^T : B(k=o, n=kd) = W[n*cout + k]
+                        check(L.mvk_gemm_f32(ptr(go), cout, 1, ptr(w), 1, cout, nq, kd, cout, ptr(dA), ld, 1, st))
+            else:
+                a_hi, a_lo, w_hi, w_lo = saved
+                terms = 3 if contraction == "bf16x3" else 1
+                ld, npad = a_hi.shape[1], w_hi.shape[1]
+                go_hi = torch.empty((nq, npad), dtype=torch.bfloat16, device=dev)
+                go_lo = torch.empty((nq, npad), dtype=torch.bfloat16, device=dev)
+                check(L.mvk_split_bf16(ptr(go), nq, cout, cout, ptr(go_hi), ptr(go_lo), nq, npad, st))
+                if need_w:
+                    gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
+                    if nq > 0:
+                        kb_total = (nq + 63) // 64
+                        split = _split_k_for((kd + 127) // 128, npad // (128 if npad % 128 == 0 else 64), kb_total)
+                        # dW = A^T dOut, both operands MN-major, reduction over the points
+                        check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 1, ld, ptr(go_hi), ptr(go_lo), 1, npad,
+                                                kd, npad, nq, ptr(gw), cout, cout, terms, split, st))
+                if need_x:
+                    dA = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                    if nq > 0:
+                        # dA = dOut W^T : A = dOut [nq, npad] K-major, B = W [ld, npad] K-major
+                        check(L.mvk_gemm_bf16x3(ptr(go_hi), ptr(go_lo), 0, npad, ptr(w_hi), ptr(w_lo), 0, npad,
+                                                nq, ld, npad, ptr(dA), ld, ld, terms, 1, st))
+            if need_x:
+                gx = torch.zeros((ns, cin), dtype=torch.float32, device=dev)
+                check(L.mvk_kpconv_weighted_bwd(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, cin, ptr(kp), K,
+                                                extent, influence, aggregation, ptr(dA), ld, ptr(gx), st))
+        return None, None, None, gx, gw, None, None, None, None, None
+
+
+class KPConv(nn.Module):
+
+    def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
+                 fixed_kernel_points='center', KP_influence='linear', aggregation_mode='sum',
+                 deformable=False, modulated=False, contraction=None):
+        """
+        Initialize parameters for KPConv (same arguments as blocks.py:145-147).
+        :param kernel_size: Number of kernel points.
+        :param p_dim: dimension of the point space.
+        :param in_channels: dimension of input features.
+        :param out_channels: dimension of output features.
+        :param KP_extent: influence radius of each kernel point.
+        :param radius: radius used for kernel point init.
+        :param fixed_kernel_points: fix position of certain kernel points ('none', 'center' or 'verticals').
+        :param KP_influence: influence function of the kernel points ('constant', 'linear', 'gaussian').
+        :param aggregation_mode: choose to sum influences, or only keep the closest ('closest', 'sum').
+        :param deformable: choose deformable or not
+        :param modulated: choose if kernel weights are modulated in addition to deformed
+        :param contraction: (extension) 'bf16x3' | 'bf16' | 'fp32'; default env MVK_CONTRACTION or 'bf16x3'
+        """
+        super(KPConv, self).__init__()
+        if deformable or modulated:
+            raise NotImplementedError("deformable / modulated KPConv (blocks.py:243-325) is not implemented "
+                                      "in the B200 path yet; refusing to fall back")
+        if p_dim != 3:
+            raise NotImplementedError("the B200 path handles 3D point clouds only (p_dim=3)")
+        if KP_influence not in _INFLUENCE:
+            raise ValueError('Unknown influence function type (config.KP_influence)')
+        if aggregation_mode not in _AGGREGATION:
+            raise ValueError("Unknown convolution mode. Should be 'closest' or 'sum'")
+
+        # Save parameters
+        self.K = kernel_size
+        self.p_dim = p_dim
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.radius = radius
+        self.KP_extent = KP_extent
+        self.fixed_kernel_points = fixed_kernel_points
+        self.KP_influence = KP_influence
+        self.aggregation_mode = aggregation_mode
+        self.deformable = deformable
+        self.modulated = modulated
+        self.contraction = contraction or DEFAULT_CONTRACTION
+        if self.contraction not in CONTRACTIONS:
+            raise ValueError("contraction must be one of %r" % (CONTRACTIONS,))
+
+        # Running variables of the deformable branch, kept for attribute compatibility
+        self.min_d2 = None
+        self.deformed_KP = None
+        self.offset_features = None
+        self.offset_dim = None
+        self.offset_conv = None
+        self.offset_bias = None
+
+        # Initialize weights
+        self.weights = Parameter(torch.zeros((self.K, in_channels, out_channels), dtype=torch.float32),
+                                 requires_grad=True)
+        self.reset_parameters()
+
+        # Initialize kernel points
+        self.kernel_points = self.init_KP()
+
+    def reset_parameters(self):
+        kaiming_uniform_(self.weights, a=math.sqrt(5))
+
+    def init_KP(self):
+        """Kernel point positions in a sphere (blocks.py:221-235)."""
+        K_points_numpy = load_kernels(self.radius, self.K, dimension=self.p_dim, fixed=self.fixed_kernel_points)
+        return Parameter(torch.tensor(K_points_numpy, dtype=torch.float32), requires_grad=False)
+
+    def forward(self, q_pts, s_pts, neighb_inds, x):
+        return _KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points,
+                                     self.KP_extent, _INFLUENCE[self.KP_influence],
+                                     _AGGREGATION[self.aggregation_mode], self.contraction)
+
+    def __repr__(self):
+        return 'KPConv(radius: {:.2f}, in_feat: {:d}, out_feat: {:d})'.format(self.radius, self.in_channels,
+                                                                              self.out_channels)
+
+
+# -------------------------------------------------------------------------------------------------
+# gather pools (blocks.py:35-110)
+# -------------------------------------------------------------------------------------------------
+class _PoolFunction(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, inds, mode):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if not x.is_cuda:
+            raise RuntimeError("pool: tensors must live on a CUDA device (no CPU fallback)")
+        xf = x.detach().contiguous().float()
+        ii, is64 = _idx(inds if inds.dim() == 2 else inds.reshape(-1, 1))
+        ns, c = xf.shape
+        nq, h = ii.shape
+        out = torch.empty((nq, c), dtype=torch.float32, device=xf.device)
+        arg = torch.empty((nq, c), dtype=torch.int32, device=xf.device) if mode == 0 else None
+        with torch.cuda.device(xf.device):
+            check(L.mvk_pool(ptr(xf), ns, c, ptr(ii), is64, nq, h, mode, ptr(out), ptr(arg), stream_ptr()))
+        ctx.save_for_backward(ii, arg if arg is not None else ii)
+        ctx.cfg = (ns, c, nq, h, mode, is64)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        L = _lib.lib()
+        ii, arg = ctx.saved_tensors
+        ns, c, nq, h, mode, is64 = ctx.cfg
+        go = grad_out.detach().contiguous().float()
+        gx = torch.zeros((ns, c), dtype=torch.float32, device=go.device)
+        with torch.cuda.device(go.device):
+            check(L.mvk_pool_bwd(ptr(go), nq, c, ptr(arg) if mode == 0 else None, ptr(ii), is64, h, mode, ns,
+                                 ptr(gx), stream_ptr()))
+        return gx, None, None
+
+
+def max_pool(x, inds):
+    """Pools features with the maximum values (blocks.py:93-110).  NB: like the reference the
+    shadow row is ZERO (not -inf), so a row with shadow neighbours never pools below 0.
+    :param x: [n1, d] features matrix
+    :param inds: [n2, max_num] pooling indices
+    :return: [n2, d] pooled features matrix
+    """
+    return _PoolFunction.apply(x, inds, 0)
+
+
+def closest_pool(x, inds):
+    """Pools features from the closest neighbors (blocks.py:79-90); only the first column is used.
+    :param x: [n1, d] features matrix
+    :param inds: [n2, max_num]
+    :return: [n2, d] pooled features matrix
+    """
+    return _PoolFunction.apply(x, inds, 1)
+
+
+def gather(x, idx, method=2):
+    """x[idx] with a shadow-free index tensor (blocks.py:35-66).  All three reference `method`s
+    compute the same values; they only differ in how autograd scatters."""
+    if method not in (0, 1, 2):
+        raise ValueError('Unkown method')
+    return x[idx]

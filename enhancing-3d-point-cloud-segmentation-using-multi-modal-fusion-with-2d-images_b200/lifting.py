@@ -1,0 +1,272 @@
+"""2D -> 3D lifting ops: host-side mirror of the reference interfaces, CUDA underneath.
+
+    group_points(points, index)                      mvpnet/ops/group_points.py:5-31
+    FeatureAggregation(in_channels, mlp_channels=(64, 64, 64), reduction='sum', use_relation=True)
+                                                     mvpnet/models/mvpnet_3d.py:12-70
+    depth2xyz(cam_matrix, depth)                     datasets/ScanNet_sphere_color.py:66-72
+    unproject_views(cam_matrix, depths, poses)       :409-417 for all views of a sphere at once
+    knn_pixels(xyz64, mask, queries, k=3)            :442-452 (replaces sklearn ball-tree kNN)
+
+FeatureAggregation keeps the reference's parameter names (mlp.{i}.conv.weight, mlp.{i}.bn.*) so
+mvpnet checkpoints load with load_state_dict.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+from .geometry import _workspace
+
+
+# -------------------------------------------------------------------------------------------------
+class GroupPointsFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, index):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if not points.is_cuda:
+            raise RuntimeError("group_points: tensors must live on a CUDA device (no CPU fallback)")
+        if points.dim() != 3 or index.dim() != 3 or points.size(0) != index.size(0):
+            raise RuntimeError("group_points: expected points (b, c, n1) and index (b, n2, k)")
+        p = points.detach().contiguous().float()
+        idx = index.detach().contiguous().long()
+        b, c, n1 = p.shape
+        _, n2, k = idx.shape
+        out = torch.empty((b, c, n2, k), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            check(L.mvk_group_points(ptr(p), b, c, n1, ptr(idx), n2, k, ptr(out), stream_ptr()))
+        ctx.save_for_backward(idx)
+        ctx.num_points = n1
+        return out
+
+    @staticmethod
+    def backward(ctx, *grad_output):
+        L = _lib.lib()
+        idx = ctx.saved_tensors[0]
+        go = grad_output[0].detach().contiguous().float()
+        b, c, n2, k = go.shape
+        gi = torch.zeros((b, c, ctx.num_points), dtype=torch.float32, device=go.device)
+        with torch.cuda.device(go.device):
+            check(L.mvk_group_points_bwd(ptr(go), b, c, ctx.num_points, ptr(idx), n2, k, ptr(gi), stream_ptr()))
+        return gi, None
+
+
+def group_points(points, index):
+    """Gather points by index
+
+    Args:
+        points (torch.Tensor): (batch_size, channels, num_points)
+        index (torch.Tensor): (batch_size, num_centroids, num_neighbors), indices of neighbors of each centroid.
+
+    Returns:
+        group_points (torch.Tensor): (batch_size, channels, num_centroids, num_neighbors), grouped points.
+    """
+    return GroupPointsFunction.apply(points, index)
+
+
+# -------------------------------------------------------------------------------------------------
+class _Conv2dBNReLU(nn.Module):
+    """Parameter container with the reference's names (common/nn/modules/conv.py:29-51)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, 1, bias=False)
+        self.bn = nn.BatchNorm2d(out_channels)
+
+
+class FeatureAggregation(nn.Module):
+    """Feature Aggregation inspired by ContFuse (mvpnet_3d.py:12-70): relation features
+    [diff_xyz, |diff|^2] concatenated to the k gathered 2D features, a shared MLP of
+    1x1 conv (no bias) + BatchNorm2d + ReLU layers, then sum / max over the k neighbours.
+
+    The forward pass runs libmvk kernels: one row-GEMM per layer with the previous layer's
+    batch-norm + ReLU folded into its operand load and the batch statistics of its own output
+    accumulated on the fly (fp64), then a fused bn + relu + reduce.
+    """
+
+    def __init__(self, in_channels, mlp_channels=(64, 64, 64), reduction='sum', use_relation=True):
+        super(FeatureAggregation, self).__init__()
+        self.in_channels = in_channels
+        self.use_relation = use_relation
+        if not use_relation:
+            raise NotImplementedError("use_relation=False is not used by MV-KPConv; not implemented")
+        if mlp_channels:
+            self.out_channels = mlp_channels[-1]
+            self.mlp = nn.ModuleList()
+            c_in = in_channels + 4
+            for c_out in mlp_channels:
+                self.mlp.append(_Conv2dBNReLU(c_in, c_out))
+                c_in = c_out
+        else:
+            raise NotImplementedError("mlp_channels=() (pure reduction) is not used by MV-KPConv")
+        if reduction not in ('sum', 'max'):
+            raise ValueError("reduction must be 'sum' or 'max'")
+        self.reduction = reduction
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # common/nn/init.py:22-26 applied to every conv (mvpnet_3d.py:66-70)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_uniform_(m.weight)
+
+    # ---- device pipeline on row-major [np*k, C] activations ---------------------------------
+    def _run(self, X, np_, k):
+        L = _lib.lib()
+        dev = X.device
+        rows = np_ * k
+        st = stream_ptr()
+        scale = shift = None
+        cur, ldx = X, X.shape[1]
+        for layer in self.mlp:
+            W = layer.conv.weight.detach().reshape(layer.conv.out_channels, -1).contiguous().float()
+            cout, cin = W.shape
+            Y = torch.empty((rows, cout), dtype=torch.float32, device=dev)
+            stats = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+            check(L.mvk_fa_layer(ptr(cur), rows, cin, ldx, ptr(scale), ptr(shift), ptr(W), cout, ptr(Y),
+                                 ptr(stats), st))
+            bn = layer.bn
+            if self.training or not bn.track_running_stats:
+                mean = stats[:cout] / rows
+                var = (stats[cout:] / rows - mean * mean).clamp_min(0.0)
+                if bn.track_running_stats:
+                    with torch.no_grad():
+                        m = bn.momentum if bn.momentum is not None else 0.1
+                        unbiased = var * (rows / max(rows - 1, 1))
+                        bn.running_mean.mul_(1 - m).add_(m * mean.float())
+                        bn.running_var.mul_(1 - m).add_(m * unbiased.float())
+                        bn.num_batches_tracked += 1
+            else:
+                mean, var = bn.running_mean.double(), bn.running_var.double()
+            inv = torch.rsqrt(var + bn.eps)
+            g = bn.weight.detach().double()
+            scale = (g * inv).float().contiguous()
+            shift = (bn.bias.detach().double() - mean * g * inv).float().contiguous()
+            cur, ldx = Y, cout
+        cout = cur.shape[1]
+        out = torch.empty((cout, np_), dtype=torch.float32, device=dev)
+        check(L.mvk_fa_reduce(ptr(cur), np_, k, cout, ptr(scale), ptr(shift), 0 if self.reduction == 'sum' else 1,
+                              ptr(out), st))
+        return out
+
+    def forward(self, src_xyz, tgt_xyz, feature):
+        """
+        Args:
+            src_xyz (torch.Tensor): (batch_size, 3, num_points, k)
+            tgt_xyz (torch.Tensor): (batch_size, 3, num_points)
+            feature (torch.Tensor): (batch_size, in_channels, num_points, k)
+        Returns:
+            torch.Tensor: (batch_size, out_channels, num_points)
+        """
+        _lib.require_cuda()
+        if not feature.is_cuda:
+            raise RuntimeError("FeatureAggregation: tensors must live on a CUDA device (no CPU fallback)")
+        if torch.is_grad_enabled() and (feature.requires_grad or any(p.requires_grad for p in self.parameters())
+                                        ) and getattr(self, "_strict_grad", False):
+            raise NotImplementedError("FeatureAggregation backward is not implemented in the B200 path yet")
+        b, c, np_, k = feature.shape
+        with torch.no_grad(), torch.cuda.device(feature.device):
+            diff = (src_xyz - tgt_xyz.unsqueeze(-1)).float()
+            dist = torch.sum(diff ** 2, dim=1, keepdim=True)
+            x = torch.cat([feature.float(), diff, dist], dim=1)  # (b, c+4, np, k)
+            X = x.permute(0, 2, 3, 1).reshape(b * np_ * k, c + 4).contiguous()
+            out = self._run(X, b * np_, k)  # (cout, b*np)
+            return out.reshape(-1, b, np_).permute(1, 0, 2).contiguous()
+
+    def forward_from_maps(self, feature_2d, image_xyz, knn_indices, tgt_points):
+        """Fused entry point for the fusion nets' per-sphere loop (architectures_sphere.py:264-284):
+        gathers the k nearest pixels' features and coordinates straight from the 2D maps.
+
+        feature_2d  (C, npix)  channel-major (the reference's (b,64,nv*h*w) slice) or any strides
+        image_xyz   (npix, 3)  float32 world coordinates of the pixels
+        knn_indices (np, k)    int64 flat pixel ids
+        tgt_points  (np, 3)    float32 sphere points
+        returns     (C_out, np)
+        """
+        _lib.require_cuda()
+        L = _lib.lib()
+        c, npix = feature_2d.shape
+        np_, k = knn_indices.shape
+        dev = feature_2d.device
+        with torch.no_grad(), torch.cuda.device(dev):
+            f = feature_2d.detach().float()
+            X = torch.empty((np_ * k, c + 4), dtype=torch.float32, device=dev)
+            check(L.mvk_fa_gather(ptr(f) if f.is_contiguous() else _lib.C.c_void_p(f.data_ptr()), f.stride(0),
+                                  f.stride(1), c, ptr(image_xyz.contiguous().float()),
+                                  ptr(knn_indices.contiguous().long()), np_, k,
+                                  ptr(tgt_points.contiguous().float()), ptr(X), c + 4, stream_ptr()))
+            return self._run(X, np_, k)
+
+
+# -------------------------------------------------------------------------------------------------
+def _kinv64(cam_matrix):
+    """inv(cam_matrix[:3,:3]) exactly as the reference evaluates it on the host: the fp32 matrix is
+    inverted in fp32 (np.linalg.inv keeps float32) and only then promoted by the fp64 product."""
+    cam = np.asarray(cam_matrix)
+    return np.linalg.inv(cam[:3, :3]).astype(np.float64)
+
+
+def unproject_views(cam_matrix, depths, poses, return_f64=True):
+    """All views of one sphere: depth (nv, h, w) -> world xyz and validity.
+
+    Mirrors depth2xyz + `image_mask = z > 0` + `xyz @ pose[:3,:3].T + pose[:3,3]`
+    (ScanNet_sphere_color.py:409-417).  Returns (xyz32 [nv,h,w,3] f32, mask [nv,h,w] bool,
+    xyz64 [nv*h*w,3] f64 -- what the reference feeds to the kNN).
+    """
+    _lib.require_cuda()
+    L = _lib.lib()
+    as_np = not isinstance(depths, torch.Tensor)
+    d = torch.as_tensor(np.ascontiguousarray(depths, dtype=np.float32)) if as_np else depths
+    d = d.cuda().contiguous().float()
+    nv, h, w = d.shape
+    dev = d.device
+    P = torch.as_tensor(np.ascontiguousarray(poses, dtype=np.float32)) if not isinstance(poses, torch.Tensor) else poses
+    P = P.to(dev).contiguous().float().reshape(nv, 16)
+    kinv = torch.from_numpy(np.ascontiguousarray(_kinv64(cam_matrix if not isinstance(cam_matrix, torch.Tensor)
+                                                        else cam_matrix.cpu().numpy()))).to(dev)
+    xyz64 = torch.empty((nv * h * w, 3), dtype=torch.float64, device=dev)
+    xyz32 = torch.empty((nv, h, w, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((nv, h, w), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(L.mvk_unproject_views(ptr(kinv), ptr(d), ptr(P), nv, h, w, ptr(xyz64), ptr(xyz32), ptr(mask),
+                                    stream_ptr()))
+    maskb = mask.bool()
+    if as_np:
+        return xyz32.cpu().numpy(), maskb.cpu().numpy(), xyz64.cpu().numpy()
+    return xyz32, maskb, xyz64
+
+
+def depth2xyz(cam_matrix, depth):
+    """project depth map to 3D (camera frame), (h*w, 3) float64 like the reference
+    (ScanNet_sphere_color.py:66-72)."""
+    as_np = not isinstance(depth, torch.Tensor)
+    d = np.asarray(depth) if as_np else depth
+    eye = np.eye(4, dtype=np.float32)
+    _, _, xyz64 = unproject_views(cam_matrix, d[None] if as_np else d.unsqueeze(0), eye[None])
+    return xyz64
+
+
+def knn_pixels(xyz64, mask, queries, k=3):
+    """k nearest VALID pixels of every query point, as flat pixel ids (view*h*w + pix), sorted by
+    (distance, id); fp64 distances like sklearn's ball tree on the float64 unprojected pixels
+    (ScanNet_sphere_color.py:442-452).  Returns int64 (nq, k)."""
+    _lib.require_cuda()
+    L = _lib.lib()
+    as_np = not isinstance(queries, torch.Tensor)
+    keys = (torch.as_tensor(np.ascontiguousarray(xyz64, dtype=np.float64)) if not isinstance(xyz64, torch.Tensor)
+            else xyz64).cuda().contiguous().double().reshape(-1, 3)
+    dev = keys.device
+    m = (torch.as_tensor(np.ascontiguousarray(mask)) if not isinstance(mask, torch.Tensor) else mask)
+    m = m.to(dev).reshape(-1).to(torch.uint8).contiguous()
+    q = (torch.as_tensor(np.ascontiguousarray(queries, dtype=np.float32)) if as_np else queries)
+    q = q.to(dev).contiguous().float()
+    npix, nq = keys.shape[0], q.shape[0]
+    if int(m.sum().item()) < k:
+        raise RuntimeError("knn_pixels: fewer than k valid pixels")
+    out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        wsb = L.mvk_knn_workspace_bytes(npix, nq)
+        ws = _workspace(wsb, dev)
+        check(L.mvk_knn_pixels(ptr(keys), ptr(m), npix, ptr(q), nq, k, ptr(ws), ws.numel(), ptr(out), stream_ptr()))
+    return out.cpu().numpy() if as_np else out

@@ -1,0 +1,218 @@
+/* mvk.h -- C ABI of the B200-native MV-KPConv hot path (libmvk.so, sm_100a only).
+ *
+ * Conventions (all entry points):
+ *   - plain C: raw pointers + sizes, no torch / C++ types in any signature;
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); the library
+ *     never synchronises except inside the `*_host` convenience entry points;
+ *   - scratch memory is caller-provided: ask `*_workspace_bytes`, pass `ws`/`ws_bytes`;
+ *   - return value: 0 (MVK_OK) or a negative MVK_ERR_* code; nothing is thrown across the ABI.
+ *     `mvk_error_string` names a code, `mvk_last_cuda_error` returns the last CUDA runtime error
+ *     string seen by this thread.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * repository root).
+ */
+#ifndef MVK_H_
+#define MVK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVK_OK 0
+#define MVK_ERR_INVALID_ARG (-1)   /* bad shape / null pointer / unsupported parameter            */
+#define MVK_ERR_WORKSPACE (-2)     /* ws_bytes smaller than *_workspace_bytes                      */
+#define MVK_ERR_CUDA (-3)          /* a CUDA runtime / driver call failed (see mvk_last_cuda_error)*/
+#define MVK_ERR_RANGE (-4)         /* coordinates / sizes outside what the hashed grid can index   */
+#define MVK_ERR_UNSUPPORTED (-5)   /* mode of the reference operator not implemented here          */
+#define MVK_ERR_EMPTY (-6)         /* empty result (the reference raises RuntimeError("Error"))    */
+
+typedef void* mvk_stream_t; /* cudaStream_t */
+
+const char* mvk_error_string(int code);
+const char* mvk_last_cuda_error(void);
+int mvk_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+unsigned long long mvk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Radius neighbours.
+ * Replaces cpp_wrappers.cpp_neighbors.radius_neighbors.batch_query
+ *   KPConv-PyTorch/cpp_wrappers/cpp_neighbors/wrapper.cpp:58-238  (glue, arg contract)
+ *   KPConv-PyTorch/cpp_wrappers/cpp_neighbors/neighbors/neighbors.cpp:211-332 (batch_nanoflann_neighbors)
+ * called through datasets/common.py:185-196 (batch_neighbors).
+ *
+ * queries [nq,3] f32, supports [ns,3] f32, q_lengths/s_lengths [nb] i32 (stacked batch elements),
+ * radius f32.  A support j is a neighbour of query i iff both belong to the same batch element and
+ * ((dx*dx)+dy*dy)+dz*dz < radius*radius evaluated in fp32 WITHOUT fma contraction.  Rows are sorted
+ * by (d2, support index) ascending and padded with ns; indices are stacked (global) support indices.
+ *
+ * Two-phase protocol (the row width is data dependent):
+ *   1. mvk_neighbors_count : builds the hashed cell grid in `ws`, writes counts[nq] and
+ *                            *max_count (device int, must be zero-initialised by the callee: it is).
+ *   2. caller reads max_count (the ONLY host sync), allocates out[nq, width], width >= 1.
+ *   3. mvk_neighbors_fill  : re-uses the grid left in `ws` by phase 1 (same ws, same inputs);
+ *      max_count is the value read in step 2 (sizes the per-warp sort buffers).
+ *      width may be smaller than max_count: rows then keep their `width` NEAREST neighbours
+ *      (== the reference's big_neighborhood_filter crop, datasets/common.py:411-421).
+ * ---------------------------------------------------------------------------------------------- */
+size_t mvk_neighbors_workspace_bytes(int nq, int ns, int nb);
+int mvk_neighbors_count(const float* queries, int nq, const float* supports, int ns,
+                        const int* q_lengths, const int* s_lengths, int nb, float radius, void* ws,
+                        size_t ws_bytes, int* counts, int* max_count, mvk_stream_t stream);
+int mvk_neighbors_fill(const float* queries, int nq, const float* supports, int ns,
+                       const int* q_lengths, const int* s_lengths, int nb, float radius, void* ws,
+                       size_t ws_bytes, int max_count, int width, int* out, mvk_stream_t stream);
+/* Same with 64-bit output (the dtype the reference model consumes, datasets/common.py:874-876). */
+int mvk_neighbors_fill_i64(const float* queries, int nq, const float* supports, int ns,
+                           const int* q_lengths, const int* s_lengths, int nb, float radius,
+                           void* ws, size_t ws_bytes, int max_count, int width, long long* out,
+                           mvk_stream_t stream);
+/* Host-buffer convenience entry point == the reference call: all pointers are HOST pointers,
+ * *out_host is malloc'ed [nq, *width] int32 (free with mvk_free_host).  Copies H2D, runs both
+ * phases on the default stream, copies D2H.  Returns MVK_ERR_EMPTY when nq * max_count == 0
+ * (wrapper.cpp:201-205). */
+int mvk_batch_neighbors_host(const float* queries_host, int nq, const float* supports_host, int ns,
+                             const int* q_lengths_host, const int* s_lengths_host, int nb,
+                             float radius, int** out_host, int* width);
+void mvk_free_host(void* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grid subsampling (voxel barycentres).
+ * Replaces cpp_wrappers.cpp_subsampling.grid_subsampling.subsample / subsample_batch
+ *   KPConv-PyTorch/cpp_wrappers/cpp_subsampling/wrapper.cpp:62-333, 338-566 (glue)
+ *   KPConv-PyTorch/cpp_wrappers/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-210
+ * called through datasets/common.py:44-182.
+ *
+ * points [n,3] f32, features [n,fdim] f32 or NULL, labels [n,ldim] i32 or NULL (ldim <= 1 in batch
+ * mode, like the reference's usable range), lengths [nb] i32, sampleDl f32, max_p (<1 = no limit).
+ * Outputs are sized for the worst case (n rows); out_lengths[nb] receives the per-element counts
+ * (after max_p), *out_total (device int) their sum.  Output order is the reference's emission
+ * order (libstdc++ unordered_map iteration order), bit-exact fp32 barycentres.
+ * ---------------------------------------------------------------------------------------------- */
+size_t mvk_subsample_workspace_bytes(int n, int nb, int fdim, int ldim);
+int mvk_grid_subsample(const float* points, int n, const float* features, int fdim,
+                       const int* labels, int ldim, const int* lengths, int nb, float sampleDl,
+                       int max_p, void* ws, size_t ws_bytes, float* out_points,
+                       float* out_features, int* out_labels, int* out_lengths, int* out_total,
+                       mvk_stream_t stream);
+/* Per-element rotation used by batch_grid_subsampling(random_grid_orient=True),
+ * datasets/common.py:114-119 and :131-135:  out[i, c] = (p[i,0]*R[0,c] + p[i,1]*R[1,c]) + p[i,2]*R[2,c]
+ * in fp32 without contraction (numpy's multiply-then-sum order); transpose != 0 applies R^T.
+ * rot [nb, 9] f32 row-major.  In-place allowed (out == points). */
+int mvk_rotate_batch(const float* points, int n, const int* lengths, int nb, const float* rot,
+                     int transpose, float* out, mvk_stream_t stream);
+/* Host-buffer convenience entry point (outputs malloc'ed; free with mvk_free_host). */
+int mvk_grid_subsample_host(const float* points_host, int n, const float* features_host, int fdim,
+                            const int* labels_host, int ldim, const int* lengths_host, int nb,
+                            float sampleDl, int max_p, float** out_points_host,
+                            float** out_features_host, int** out_labels_host,
+                            int* out_lengths_host, int* out_total);
+
+/* ------------------------------------------------------------------------------------------------
+ * KPConv (rigid) forward / backward.
+ * Replaces the ATen op chain of KPConv.forward, KPConv-PyTorch/models/blocks.py:277-374, and its
+ * autograd.  out[i,:] = sum_k ( sum_h w_ihk x[j_ih,:] ) W[k]   with shadow index j == ns.
+ *
+ * Stage A  (gather + kernel-point influence, HBM/L2 bound):
+ *      weighted[i, k*cin + c] = sum_h w_ihk * x[j_ih, c]
+ *   written either as fp32 [nq, ld] (contraction "fp32") or as a bf16 hi/lo pair [nq, ld] each
+ *   (hi = bf16(v), lo = bf16(v - hi)) for the tensor-core contraction.  ld >= 15*cin, pad zeroed.
+ * Stage B  (contraction [nq, 15*cin] x [15*cin, cout]): mvk_gemm_* below.
+ *
+ * influence: 0 constant, 1 linear, 2 gaussian (blocks.py:329-346); aggregation: 0 sum, 1 closest
+ * (:349-354).  idx_is_i64: neighb_inds dtype (the reference passes int64).
+ * ---------------------------------------------------------------------------------------------- */
+int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                        int idx_is_i64, int h, const float* x, int cin, const float* kernel_points,
+                        int num_kp, float kp_extent, int influence, int aggregation, int ld,
+                        float* out_f32, void* out_hi_bf16, void* out_lo_bf16, mvk_stream_t stream);
+/* Backward of stage A w.r.t. x:  grad_x[j, c] += sum_k w_ihk * grad_weighted[i, k*cin + c]
+ * (grad_x [ns, cin] must be zero-initialised by the caller; fp32 atomics). */
+int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int ns,
+                            const void* neighb_inds, int idx_is_i64, int h, int cin,
+                            const float* kernel_points, int num_kp, float kp_extent, int influence,
+                            int aggregation, const float* grad_weighted, int ld, float* grad_x,
+                            mvk_stream_t stream);
+
+/* fp32 -> bf16 hi/lo split of a [rows, cols] matrix into zero-padded [rows_pad, ld] buffers. */
+int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, void* lo, int rows_pad,
+                   int ld, mvk_stream_t stream);
+
+/* Tensor-core contraction (tcgen05 + TMA, fp32 accumulation in TMEM):
+ *      D[m, n] (+)= sum_k A(m,k) * B(k,n)          for m < M, n < n_valid
+ * Operands are bf16 hi/lo pairs; terms = 3 evaluates hi*hi + lo*hi + hi*lo (fp32-grade, ~2^-16
+ * relative), terms = 1 evaluates hi*hi only (plain bf16).
+ *   a_mn_major = 0: A stored [M, lda] (K contiguous);   1: A stored [K, lda] (M contiguous)
+ *   b_mn_major = 0: B stored [N, ldb] (K contiguous);   1: B stored [K, ldb] (N contiguous)
+ * K must be a multiple of 64 unless the k extent is covered by zero padding up to one (see
+ * DESIGN.md); N (operand extent, >= n_valid) a multiple of 64, lda/ldb multiples of 8.
+ * split_k > 1 partitions K over CTAs and accumulates into D with fp32 atomics (D must be zeroed). */
+int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
+                    const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
+                    int n_valid, int terms, int split_k, mvk_stream_t stream);
+/* Strict fp32 SIMT contraction with arbitrary strides:
+ *      D[m, n] (+)= sum_k A[m*a_rs + k*a_cs] * B[k*b_rs + n*b_cs]                                */
+int mvk_gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B, long long b_rs,
+                 long long b_cs, int M, int N, int K, float* D, int ldd, int split_k,
+                 mvk_stream_t stream);
+
+/* Gather pools on the neighbour matrices (blocks.py:79-110): mode 0 = max_pool (zero-padded
+ * shadow row!), 1 = closest_pool (first column).  arg_out [nq, c] i32 (max_pool only) records the
+ * winning support row for the backward.  Backward: grad_x[arg] += grad_out. */
+int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, int nq, int h, int mode,
+             float* out, int* arg_out, mvk_stream_t stream);
+int mvk_pool_bwd(const float* grad_out, int nq, int c, const int* arg, const void* inds,
+                 int idx_is_i64, int h, int mode, int ns, float* grad_x, mvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2D -> 3D lifting.
+ *   mvk_unproject_views : KPConv-PyTorch/datasets/ScanNet_sphere_color.py:66-72 (depth2xyz) and
+ *                         :409-417 (valid mask, camera->world), fp64 arithmetic like numpy.
+ *   mvk_knn_pixels      : :442-452 (sklearn NearestNeighbors(k, 'ball_tree') on the valid pixels,
+ *                         remapped to flat pixel ids view*h*w + pix), fp64 distances.
+ *   mvk_group_points    : mvpnet/ops/group_points.py:5-31, mvpnet/ops/cuda/group_points_kernel.cu:25-144.
+ *   mvk_feature_aggregation_* : mvpnet/models/mvpnet_3d.py:40-64 (+ common/nn/modules/mlp.py:38-75).
+ * ---------------------------------------------------------------------------------------------- */
+/* kinv [9] f64 row-major (= inv(cam_matrix[:3,:3]) computed by the host mirror exactly like the
+ * reference, in fp32 then widened), depth [nv,h,w] f32, pose [nv,16] f32 row-major 4x4.
+ * Outputs: xyz64 [nv*h*w,3] f64 (what the reference feeds to the kNN), xyz32 [nv*h*w,3] f32
+ * (what the reference stacks into the batch), mask [nv*h*w] u8. */
+int mvk_unproject_views(const double* kinv, const float* depth, const float* pose, int nv, int h,
+                        int w, double* xyz64, float* xyz32, unsigned char* mask, mvk_stream_t stream);
+size_t mvk_knn_workspace_bytes(int npix, int nq);
+/* keys: xyz64 [npix,3] + mask [npix]; queries [nq,3] f32; out [nq,k] i64 flat pixel ids sorted by
+ * (distance, pixel id); k <= 8. */
+int mvk_knn_pixels(const double* xyz64, const unsigned char* mask, int npix, const float* queries,
+                   int nq, int k, void* ws, size_t ws_bytes, long long* out, mvk_stream_t stream);
+/* points [b,c,n1] f32, index [b,n2,k] i64 -> out [b,c,n2,k]. */
+int mvk_group_points(const float* points, int b, int c, int n1, const long long* index, int n2, int k,
+                     float* out, mvk_stream_t stream);
+int mvk_group_points_bwd(const float* grad_out, int b, int c, int n1, const long long* index, int n2,
+                         int k, float* grad_points, mvk_stream_t stream);
+/* One SharedMLP layer over rows:  Y[r, o] = sum_c act(X[r, c]) * W[o, c]   where act applies the
+ * PREVIOUS layer's folded batch-norm + ReLU (scale/shift [cin], NULL = identity), and accumulates
+ * per-channel sum / sum-of-squares of Y into stats[2*cout] (f64, zero-initialised) for the
+ * batch statistics of THIS layer.  rows = np*k. */
+int mvk_fa_layer(const float* X, int rows, int cin, int ldx, const float* in_scale,
+                 const float* in_shift, const float* W, int cout, float* Y, double* stats,
+                 mvk_stream_t stream);
+/* Builds the first-layer input rows [np*k, cin+4] = [feature, diff_xyz, dist] (mvpnet_3d.py:53-57)
+ * directly from the 2D feature map: feat2d either channel-major [c, npix] (chan_stride = npix,
+ * pix_stride = 1: the reference layout) or pixel-major; src xyz taken from xyz32 [npix,3]. */
+int mvk_fa_gather(const float* feat2d, long long chan_stride, long long pix_stride, int c,
+                  const float* xyz32, const long long* knn, int np, int k, const float* tgt_xyz,
+                  float* X, int ldx, mvk_stream_t stream);
+/* Final: out[o, p] = reduce_k relu(bn(Y[p*k + kk, o]))   (reduction 0 = sum, 1 = max), written
+ * channel-major [cout, np] like the reference output (b=1). */
+int mvk_fa_reduce(const float* Y, int np, int k, int cout, const float* scale, const float* shift,
+                  int reduction, float* out, mvk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVK_H_ */

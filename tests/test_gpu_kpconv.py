@@ -1,0 +1,175 @@
+"""GPU parity: KPConv forward / backward against the reference goldens and the torch fp32 oracle.
+
+Tolerance (north_star): fp32 features and gradients within 1e-4 RELATIVE, measured as
+max|a-b| / max|b| over the tensor, for the "fp32" (strict FFMA) and "bf16x3" (tcgen05, hi/lo split
+bf16 operands, fp32 accumulation) contractions.  The plain "bf16" tensor-core contraction is stated
+separately at 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import bumpy_cloud, load_golden
+from oracle import geom, modules
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16x3": 1e-4, "bf16": 2e-2}
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def run_case(mvk, c, contraction, idx_dtype=torch.int64):
+    np.random.seed(0)
+    cin, cout = c["weights"].shape[1:]
+    conv = mvk.KPConv(15, 3, cin, cout, float(c["KP_extent"]), float(c["radius"]), KP_influence=str(c["influence"]),
+                      aggregation_mode=str(c["aggregation"]), contraction=contraction).cuda()
+    with torch.no_grad():
+        conv.weights.copy_(torch.from_numpy(c["weights"]))
+        conv.kernel_points.copy_(torch.from_numpy(c["kernel_points"]))
+    x = torch.from_numpy(c["x"]).cuda().requires_grad_(True)
+    out = conv(torch.from_numpy(c["q_pts"]).cuda(), torch.from_numpy(c["s_pts"]).cuda(),
+               torch.from_numpy(c["inds"]).cuda().to(idx_dtype), x)
+    out.backward(torch.from_numpy(c["grad_out"]).cuda())
+    return out, x.grad, conv.weights.grad
+
+
+@pytest.mark.parametrize("contraction", ["fp32", "bf16x3", "bf16"])
+def test_kpconv_vs_reference_golden(mvk, contraction):
+    g = load_golden("kpconv")
+    for name, c in g.items():
+        if name.startswith("_"):
+            continue
+        out, gx, gw = run_case(mvk, c, contraction)
+        tol = TOL[contraction]
+        assert out.shape == c["out"].shape
+        assert rel_err(out, c["out"]) < tol, (name, "out")
+        assert rel_err(gx, c["grad_x"]) < tol, (name, "grad_x")
+        assert rel_err(gw, c["grad_w"]) < tol, (name, "grad_w")
+
+
+def test_kpconv_int32_indices_equal_int64(mvk):
+    c = load_golden("kpconv")["rigid_16_32"]
+    a = run_case(mvk, c, "fp32", torch.int64)
+    b = run_case(mvk, c, "fp32", torch.int32)
+    assert torch.equal(a[0], b[0])
+
+
+@pytest.mark.parametrize("cin,cout,n,strided", [(32, 32, 6000, False), (64, 64, 5000, True), (128, 128, 1500, False),
+                                                (256, 256, 700, False), (4, 64, 4000, False), (66, 64, 3000, False)])
+def test_kpconv_vs_oracle_seeded(mvk, cin, cout, n, strided):
+    """Layer shapes of the baseline / fusion nets on real neighbourhoods."""
+    rng = np.random.default_rng(cin * 1000 + cout)
+    s_pts = bumpy_cloud(rng, n)
+    lens = np.array([n // 2, n - n // 2], np.int32)
+    radius = 0.12
+    if strided:
+        q_pts, q_lens = geom.grid_subsample_batch(s_pts, lens, sampleDl=radius / 2.5 * 2)
+    else:
+        q_pts, q_lens = s_pts, lens
+    inds = geom.batch_neighbors(q_pts, s_pts, q_lens, lens, radius).astype(np.int64)
+    extent = radius * 1.2 / 2.5
+    np.random.seed(1)
+    torch.manual_seed(1)
+    conv = mvk.KPConv(15, 3, cin, cout, extent, radius).cuda()
+    x = torch.randn(n, cin)
+    go = torch.randn(len(q_pts), cout)
+    # oracle (CPU fp32, autograd)
+    xo = x.clone().requires_grad_(True)
+    wo = conv.weights.detach().cpu().clone().requires_grad_(True)
+    oo = modules.kpconv_forward(torch.from_numpy(q_pts), torch.from_numpy(s_pts), torch.from_numpy(inds), xo,
+                                conv.kernel_points.detach().cpu(), wo, extent)
+    oo.backward(go)
+    for contraction in ("fp32", "bf16x3"):
+        conv.contraction = contraction
+        conv.weights.grad = None
+        xg = x.cuda().requires_grad_(True)
+        out = conv(torch.from_numpy(q_pts).cuda(), torch.from_numpy(s_pts).cuda(), torch.from_numpy(inds).cuda(), xg)
+        out.backward(go.cuda())
+        assert rel_err(out, oo) < 1e-4, contraction
+        assert rel_err(xg.grad, xo.grad) < 1e-4, contraction
+        assert rel_err(conv.weights.grad, wo.grad) < 1e-4, contraction
+
+
+def test_kpconv_linearity_and_shadow_rows(mvk):
+    """Size-independent properties at a BASELINE-sized layer (20k points, 64->128): linear in x,
+    rows whose neighbours are all shadows are exactly zero."""
+    rng = np.random.default_rng(9)
+    n = 20000
+    pts = bumpy_cloud(rng, n, extent=2.0)
+    lens = np.array([n], np.int32)
+    inds = torch.from_numpy(mvk.batch_neighbors(pts, pts, lens, lens, 0.1).astype(np.int64)).cuda()
+    inds[:100] = n  # all-shadow rows
+    np.random.seed(2)
+    conv = mvk.KPConv(15, 3, 64, 128, 0.048, 0.1).cuda()
+    p = torch.from_numpy(pts).cuda()
+    x1, x2 = torch.randn(n, 64, device="cuda"), torch.randn(n, 64, device="cuda")
+    with torch.no_grad():
+        y1, y2, y12 = conv(p, p, inds, x1), conv(p, p, inds, x2), conv(p, p, inds, 2 * x1 - 3 * x2)
+    assert torch.count_nonzero(y1[:100]) == 0
+    assert rel_err(y12, 2 * y1 - 3 * y2) < 1e-4
+
+
+def test_pools_vs_reference_golden(mvk):
+    g = load_golden("pools")
+    x = torch.from_numpy(g["x"]).cuda().requires_grad_(True)
+    inds = torch.from_numpy(g["inds"]).cuda()
+    mp = mvk.max_pool(x, inds)
+    assert np.array_equal(mp.detach().cpu().numpy(), g["max_pool"])
+    assert np.array_equal(mvk.closest_pool(x, inds).detach().cpu().numpy(), g["closest_pool"])
+    # backward vs torch autograd of the oracle
+    go = torch.randn_like(mp)
+    mp.backward(go)
+    xo = torch.from_numpy(g["x"]).requires_grad_(True)
+    modules.max_pool(xo, torch.from_numpy(g["inds"])).backward(go.cpu())
+    assert np.allclose(x.grad.cpu().numpy(), xo.grad.numpy(), atol=1e-6)
+    x.grad = None
+    cp = mvk.closest_pool(x, inds)
+    cp.backward(go)
+    xo.grad = None
+    modules.closest_pool(xo, torch.from_numpy(g["inds"])).backward(go.cpu())
+    assert np.allclose(x.grad.cpu().numpy(), xo.grad.numpy(), atol=1e-6)
+
+
+def test_gemm_tc_against_fp64(mvk):
+    """The tcgen05 contraction alone, all three operand-layout variants, against an fp64 product."""
+    L = mvk._lib.lib()
+    from mvkpconv_b200._lib import check, ptr, stream_ptr
+    torch.manual_seed(0)
+
+    def split(t, rows_pad, ld):
+        hi = torch.empty((rows_pad, ld), dtype=torch.bfloat16, device="cuda")
+        lo = torch.empty_like(hi)
+        check(L.mvk_split_bf16(ptr(t), t.shape[0], t.shape[1], t.shape[1], ptr(hi), ptr(lo), rows_pad, ld, stream_ptr()))
+        return hi, lo
+
+    M, N, K = 1000, 128, 960
+    A = torch.randn(M, K, device="cuda")
+    B = torch.randn(K, N, device="cuda")
+    ref = (A.double() @ B.double())
+    a_hi, a_lo = split(A, M, K)
+    # K-major A x MN-major B (forward)
+    b_hi, b_lo = split(B, K, N)
+    D = torch.empty(M, N, device="cuda")
+    check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, K, ptr(b_hi), ptr(b_lo), 1, N, M, N, K, ptr(D), N, N, 3, 1, stream_ptr()))
+    assert rel_err(D, ref) < 2e-5
+    check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, K, ptr(b_hi), ptr(b_lo), 1, N, M, N, K, ptr(D), N, N, 1, 1, stream_ptr()))
+    assert rel_err(D, ref) < 2e-2
+    # K-major A x K-major B (dA product)
+    bt_hi, bt_lo = split(B.t().contiguous(), N, K)
+    D.zero_()
+    check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, K, ptr(bt_hi), ptr(bt_lo), 0, K, M, N, K, ptr(D), N, N, 3, 1, stream_ptr()))
+    assert rel_err(D, ref) < 2e-5
+    # MN-major A x MN-major B, split-K with atomics (dW product): D2[K2, N] = A^T[K, M] ... reuse shapes
+    At = A.t().contiguous()                      # [K, M] : logical A2 = At^T? use A2 (M2=K rows) = A^T
+    at_hi, at_lo = split(A, M, K)                # stored [k2=M, m2=K] with m2 contiguous -> MN-major operand for M2=K
+    G = torch.randn(M, N, device="cuda")         # stored [k2=M, n=N]
+    g_hi, g_lo = split(G, M, N)
+    ref2 = A.double().t() @ G.double()           # [K, N]
+    D2 = torch.zeros(K, N, device="cuda")
+    check(L.mvk_gemm_bf16x3(ptr(at_hi), ptr(at_lo), 1, K, ptr(g_hi), ptr(g_lo), 1, N, K, N, M, ptr(D2), N, N, 3, 4, stream_ptr()))
+    assert rel_err(D2, ref2) < 2e-5
