@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the MV-KPConv hot path on B200 (contract: see the task statement / DESIGN.md §5).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1]): the KPConv baseline encoder-decoder of train_ScanNet_baseline
+(14 rigid KPConv layers, 24.4 M parameters) forward + backward + SGD step on a stacked batch of 8
+synthetic ScanNet-shaped spheres (r = 2 m, first_subsampling_dl = 0.04, K = 15) per GPU.  One
+"step" is one pass of the hot path over one batch: the 5-level input pyramid (3 radius-neighbour
+calls + 1 grid subsampling per level, on the GPU), the network forward, the loss, the backward
+and the optimiser update.  Metric: stacked input points processed per second (whole job).
+
+  value : inputs already resident in HBM when the timed region starts.
+  e2e   : the same step fed from pinned HOST buffers (points, features, labels copied H2D every
+          step) and ending with the loss read back to the host.
+Weak scaling: every rank gets its own batch of 8 spheres (sharded by sphere); the only collective
+is the DDP gradient all-reduce (NCCL).
+
+--impl reference times the reference's CPU path (the unmodified reference C++ in oracle/_ref for
+the pyramid + the torch-CPU restatement of KPConv for the network) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "KPConv fwd+bwd points/s"
+UNIT = "points/s"
+IN_RADIUS = 2.0
+FIRST_DL = 0.04
+SPHERES_PER_GPU = 8
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def host_features(pts):
+    # in_features_dim = 2: constant 1 + height (train_ScanNet_baseline.py:183)
+    return np.concatenate([np.ones((len(pts), 1), np.float32), pts[:, 2:3]], 1).astype(np.float32)
+
+
+# =================================================================================================
+# B200 arm
+# =================================================================================================
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import mvkpconv_b200 as mvk
+    from mvkpconv_b200 import _lib, harness, pyramid, synthetic
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # ---------------- synthetic batch of this rank (host side, untimed) ----------------
+    sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)  # first_subsampling_dl on the GPU
+    spheres = synthetic.make_spheres(SPHERES_PER_GPU, sub, seed=100 * rank, in_radius=IN_RADIUS, first_dl=FIRST_DL)
+    pts_h, lens_h = synthetic.stack(spheres)
+    n_pts = len(pts_h)
+    feats_h = host_features(pts_h)
+    labels_h = np.random.default_rng(rank).integers(0, 20, n_pts).astype(np.int64)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    pts_p, feats_p, labels_p, lens_p = pin(pts_h), pin(feats_h), pin(labels_h), pin(lens_h)
+
+    cfg = pyramid.baseline_config(in_radius=IN_RADIUS, first_subsampling_dl=FIRST_DL)
+    pts_d, lens_d = pts_p.to(dev), lens_p.to(dev)
+    cfg.neighborhood_limits = pyramid.calibrate_neighborhood_limits(pts_d, lens_d, cfg)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = harness.KPFCNN(cfg).to(dev)
+    for m in net.kpconv_layers():
+        m.contraction = args.contraction
+    model = net
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local])
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3)
+    feats_d, labels_d = feats_p.to(dev), labels_p.to(dev)
+    queries_per_step = [0]
+
+    def step(from_host):
+        if from_host:
+            p = pts_p.to(dev, non_blocking=True)
+            f = feats_p.to(dev, non_blocking=True)
+            y = labels_p.to(dev, non_blocking=True)
+            ln = lens_p.to(dev, non_blocking=True)
+        else:
+            p, f, y, ln = pts_d, feats_d, labels_d, lens_d
+        np.random.seed(1)  # batch_grid_subsampling draws its grid orientations from np.random
+        pyr = pyramid.build_pyramid(p, ln, cfg)
+        batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools,
+                                upsamples=pyr.upsamples, lengths=pyr.lengths, features=f, labels=y)
+        queries_per_step[0] = sum(t.shape[0] for t in pyr.neighbors + pyr.pools + pyr.upsamples)
+        out = model(batch)
+        loss = net.loss(out, y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)  # utils/trainer.py:191-193
+        opt.step()
+        return loss.item() if from_host else loss
+
+    def timed(from_host, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            step(from_host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        l0 = L.mvk_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = step(from_host)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, L.mvk_launch_count() - l0, clocks, float(last)
+
+    ms, launches, clocks, loss_v = timed(False, args.steps, args.warmup, sample_clocks=True)
+    ms_e2e, _, _, _ = timed(True, args.steps, max(1, args.warmup // 2))
+
+    # ---------------- per-kernel timing inside a timed region (roofline) ----------------
+    torch.cuda.synchronize()
+    with _lib.profile() as records:
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pe0.record()
+        for _ in range(args.steps):
+            step(False)
+        pe1.record()
+        torch.cuda.synchronize()
+    prof_ms = pe0.elapsed_time(pe1)
+    agg = {}
+    for name, a, s, e in records:
+        d = s.elapsed_time(e)
+        key = name
+        work = 0.0
+        if name == "mvk_kpconv_weighted":
+            nq, is64, h, cin, K, ld = a[1], a[5], a[6], a[8], a[10], a[14]
+            key += f"[cin={cin}]"
+            # B_gi = H (idx + 12 + 4 Cin) + 12 read, + 4*15*Cin staged write (hi+lo bf16 = 4 B/elem)
+            work = nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld)
+        elif name == "mvk_kpconv_weighted_bwd":
+            nq, is64, h, cin, K, ld = a[1], a[5], a[6], a[7], a[9], a[14]
+            key += f"[cin={cin}]"
+            work = nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld)
+        elif name == "mvk_gemm_bf16x3":
+            M, N, K, terms = a[8], a[9], a[10], a[14]
+            key += f"[{'x'.join(map(str, (N, K)))}]"
+            work = 2.0 * M * N * K * terms
+        r = agg.setdefault(key, [0.0, 0, 0.0, name])
+        r[0] += d
+        r[1] += 1
+        r[2] += work
+    by_entry = {}
+    for key, (d, c, w, name) in agg.items():
+        r = by_entry.setdefault(name, [0.0, 0, 0.0])
+        r[0] += d
+        r[1] += c
+        r[2] += w
+    pk, pk_kind = peaks()
+    top = max(((n, v) for n, v in by_entry.items() if v[2] > 0), key=lambda kv: kv[1][0], default=None)
+    roofline = None
+    if top is not None:
+        name, (d, c, w) = top
+        if name == "mvk_gemm_bf16x3":
+            ach = w / (d * 1e-3) / 1e12
+            roofline = {"kernel": "gemm_tc_kernel (" + name + ")", "bound": "tensor", "achieved": round(ach, 2),
+                        "peak": pk["bf16_tflops_sustained"], "peak_kind": pk_kind + " sustained bf16", "unit": "TFLOP/s",
+                        "frac": round(ach / pk["bf16_tflops_sustained"], 4), "traffic": None}
+        else:
+            ach = w / (d * 1e-3) / 1e9
+            kern = "kp_weighted_fwd" if name == "mvk_kpconv_weighted" else "kp_weighted_bwd"
+            roofline = {"kernel": kern + " (" + name + ")", "bound": "hbm", "achieved": round(ach, 1),
+                        "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4),
+                        "traffic": None}
+        roofline["launches"] = c
+        roofline["avg_launch_us"] = round(1e3 * d / c, 2)
+        roofline["share_of_step"] = round(d / prof_ms, 4)
+    breakdown = {n: {"ms_per_step": round(v[0] / args.steps, 3), "calls_per_step": v[1] // args.steps}
+                 for n, v in sorted(by_entry.items(), key=lambda kv: -kv[1][0])}
+    nb_ms = sum(v[0] for n, v in by_entry.items() if n.startswith("mvk_neighbors"))
+    nb_qps = queries_per_step[0] * args.steps / (nb_ms * 1e-3) if nb_ms > 0 else None
+
+    total_pts = n_pts  # weak scaling: every rank holds its own 8 spheres (sizes differ slightly by seed)
+    if world > 1:
+        t = torch.tensor([float(n_pts)], device=dev)
+        dist.all_reduce(t)
+        total_pts = int(t.item())
+    if rank == 0:
+        h2d = pts_p.numel() * 4 + feats_p.numel() * 4 + labels_p.numel() * 8 + lens_p.numel() * 4
+        line = {
+            "metric": METRIC, "value": round(total_pts * args.steps / (ms * 1e-3), 1), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "contraction": args.contraction, "data": "synthetic",
+            "config": {"workload": "configs[1]: KPConv baseline encoder-decoder (train_ScanNet_baseline shape, 14 KPConv "
+                                   "layers, 24.4M params) pyramid + fwd + bwd + SGD, 8 synthetic spheres/GPU",
+                       "spheres_per_gpu": SPHERES_PER_GPU, "points_per_gpu": n_pts, "in_radius": IN_RADIUS,
+                       "first_subsampling_dl": FIRST_DL, "K": 15, "neighborhood_limits": cfg.neighborhood_limits,
+                       "parallelism": f"sphere-sharded x{world}, DDP grad all-reduce" if world > 1 else "single GPU",
+                       "l2": "per-step working set (saved [N,15*Cin] operands, >1 GB) far exceeds the 126 MB L2; no flush"},
+            "e2e": {"value": round(total_pts * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
+                    "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4 + 4 * 15},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "neighbor_queries_per_s": round(nb_qps, 1) if nb_qps else None,
+            "neighbor_queries_per_step": int(queries_per_step[0]),
+            "breakdown_ms": breakdown, "loss": loss_v,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(steps=2, warmup=1, seed=0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# =================================================================================================
+# CPU reference arm / cpu_baseline leg.  The ONLY code in this file that touches oracle/.
+# =================================================================================================
+def cpu_reference(steps, warmup, seed=0, n_spheres=1):
+    """The reference's CPU path on a bounded sample of the workload: `n_spheres` of the batch's
+    spheres; pyramid by the unmodified reference C++ (oracle/_ref, one thread like the reference's
+    workers), network forward+backward+SGD on torch CPU with all host threads."""
+    from mvkpconv_b200 import harness, pyramid, synthetic
+    from oracle import geom, modules
+
+    kind = "reference" if geom.have_ref() else "port"
+    nbr = geom.ref_batch_neighbors if geom.have_ref() else geom.batch_neighbors
+    gsub = geom.ref_grid_subsample_batch if geom.have_ref() else geom.grid_subsample_batch
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sub = lambda p, dl: gsub(p, np.array([len(p)], np.int32), sampleDl=dl)[0]
+    spheres = synthetic.make_spheres(n_spheres, sub, seed=seed, in_radius=IN_RADIUS, first_dl=FIRST_DL)
+    pts, lens = synthetic.stack(spheres)
+    cfg = pyramid.baseline_config(in_radius=IN_RADIUS, first_subsampling_dl=FIRST_DL)
+
+    def cpu_subsample(points, lengths, sampleDl=0.1, random_grid_orient=True):
+        return gsub(points, lengths, sampleDl=sampleDl)
+
+    gops = SimpleNamespace(batch_neighbors=nbr, batch_grid_subsampling=cpu_subsample)
+    cfg.neighborhood_limits = pyramid.calibrate_neighborhood_limits(pts, lens, cfg, ops=gops)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    mops = SimpleNamespace(KPConv=modules.KPConvOracle, max_pool=modules.max_pool, closest_pool=modules.closest_pool)
+    net = harness.KPFCNN(cfg, ops=mops)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3)
+    feats = torch.from_numpy(host_features(pts))
+    labels = torch.from_numpy(np.random.default_rng(0).integers(0, 20, len(pts)).astype(np.int64))
+    t_pyr = t_net = 0.0
+
+    def step():
+        nonlocal t_pyr, t_net
+        t0 = time.perf_counter()
+        pyr = pyramid.build_pyramid(pts, lens, cfg, ops=gops, random_grid_orient=False)
+        t1 = time.perf_counter()
+        as_t = lambda lst, dt: [torch.from_numpy(np.ascontiguousarray(a)).to(dt) for a in lst]
+        batch = SimpleNamespace(points=as_t(pyr.points, torch.float32), neighbors=as_t(pyr.neighbors, torch.int64),
+                                pools=as_t(pyr.pools, torch.int64), upsamples=as_t(pyr.upsamples, torch.int64),
+                                lengths=pyr.lengths, features=feats, labels=labels)
+        out = net(batch)
+        loss = net.loss(out, labels)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)
+        opt.step()
+        t2 = time.perf_counter()
+        t_pyr += t1 - t0
+        t_net += t2 - t1
+        return float(loss)
+
+    for _ in range(warmup):
+        step()
+    t_pyr = t_net = 0.0
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": round(len(pts) * steps / dt, 1), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n_spheres} of the {SPHERES_PER_GPU} spheres of one batch ({len(pts)} points), {steps} steps after "
+                      f"{warmup} warm-up; pyramid: unmodified reference C++ (1 thread), network: torch CPU ({cores} threads)",
+            "ms_per_step": round(1e3 * dt / steps, 1), "ms_pyramid": round(1e3 * t_pyr / steps, 1),
+            "ms_network": round(1e3 * t_net / steps, 1), "points": int(len(pts))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU reference; the other ranks exit 0 without work
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
+    base = cpu_reference(steps=args.steps, warmup=args.warmup, seed=0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: KPConv baseline encoder-decoder (train_ScanNet_baseline shape, 14 KPConv "
+                               "layers, 24.4M params) pyramid + fwd + bwd + SGD; CPU arm on a bounded sample",
+                   "in_radius": IN_RADIUS, "first_subsampling_dl": FIRST_DL, "K": 15},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--contraction", default=os.environ.get("MVK_CONTRACTION", "bf16x3"),
+                    choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

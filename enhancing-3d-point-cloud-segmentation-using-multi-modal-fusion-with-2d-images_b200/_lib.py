@@ -53,6 +53,50 @@ def lib_path():
     return _build.LIB
 
 
+class _ProfiledLib:
+    """Proxy around the ctypes handle that brackets every C-ABI call with CUDA events on the
+    current stream (the stream the kernels are launched on).  Used by bench.py to measure the
+    per-kernel durations INSIDE the timed region; never active otherwise."""
+
+    def __init__(self, handle, records):
+        self._h, self._r = handle, records
+
+    def __getattr__(self, name):
+        fn = getattr(self._h, name)
+        if not name.startswith("mvk_") or name in ("mvk_error_string", "mvk_last_cuda_error", "mvk_version",
+                                                   "mvk_launch_count", "mvk_free_host") or name.endswith("_bytes"):
+            return fn
+        import torch
+
+        def wrapped(*args):
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self._r.append((name, args, e0, e1))
+            return rc
+
+        return wrapped
+
+
+_PROFILE_RECORDS = None
+
+
+class profile:
+    """with _lib.profile() as records: ...   -> list of (entry point, args, start event, end event)."""
+
+    def __enter__(self):
+        global _PROFILE_RECORDS
+        _PROFILE_RECORDS = []
+        return _PROFILE_RECORDS
+
+    def __exit__(self, *exc):
+        global _PROFILE_RECORDS
+        _PROFILE_RECORDS = None
+        return False
+
+
 def lib():
     """Load (building first if stale and nvcc is present).  Raises if the CUDA library is unavailable."""
     global _LIB
@@ -71,6 +115,8 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _LIB = handle
+    if _PROFILE_RECORDS is not None:
+        return _ProfiledLib(_LIB, _PROFILE_RECORDS)
     return _LIB
 
 

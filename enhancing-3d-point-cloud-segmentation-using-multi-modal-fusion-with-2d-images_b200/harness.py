@@ -1,0 +1,185 @@
+"""Model harness around the hot path: the KPFCNN encoder-decoder of the reference's baseline
+training script, composed from this package's operators.
+
+The reference architecture files (KPConv-PyTorch/models/architectures.py:189-352, blocks.py:387-695)
+are thin Python compositions of blocks; they are out of scope as a porting target, but the
+benchmark configuration ("KPConv baseline encoder-decoder, train_ScanNet_baseline shape") needs a
+driver that exists on the GPU box, where the reference tree is absent.  This harness follows the
+same block grammar ('simple', 'resnetb', 'resnetb_strided', 'nearest_upsample', 'unary') and the
+same dimension / radius bookkeeping, so its KPConv layers have exactly the shapes of SURVEY.md
+Appendix B.  KPConv / max_pool / closest_pool are this package's CUDA ops; the unary blocks
+(Linear + BatchNorm1d + LeakyReLU) are plain library layers.  The operator set is injectable so
+bench.py's CPU baseline can run the identical graph on the oracle's torch-CPU KPConv.
+"""
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import kpconv as _kp
+
+
+def product_ops():
+    return SimpleNamespace(KPConv=_kp.KPConv, max_pool=_kp.max_pool, closest_pool=_kp.closest_pool)
+
+
+class BatchNormBlock(nn.Module):
+    """blocks.py:430-466 (batch norm over the stacked points, or a bias when disabled)."""
+
+    def __init__(self, in_dim, use_bn, bn_momentum):
+        super().__init__()
+        self.use_bn = use_bn
+        if use_bn:
+            self.batch_norm = nn.BatchNorm1d(in_dim, momentum=bn_momentum)
+        else:
+            self.bias = nn.Parameter(torch.zeros(in_dim, dtype=torch.float32))
+
+    def forward(self, x):
+        return self.batch_norm(x) if self.use_bn else x + self.bias
+
+
+class UnaryBlock(nn.Module):
+    """blocks.py:469-504."""
+
+    def __init__(self, in_dim, out_dim, use_bn, bn_momentum, no_relu=False):
+        super().__init__()
+        self.mlp = nn.Linear(in_dim, out_dim, bias=False)
+        self.batch_norm = BatchNormBlock(out_dim, use_bn, bn_momentum)
+        self.no_relu = no_relu
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def forward(self, x, batch=None):
+        x = self.batch_norm(self.mlp(x))
+        return x if self.no_relu else self.leaky_relu(x)
+
+
+def _geometry(block_name, layer_ind, batch):
+    if 'strided' in block_name:
+        return batch.points[layer_ind + 1], batch.points[layer_ind], batch.pools[layer_ind]
+    return batch.points[layer_ind], batch.points[layer_ind], batch.neighbors[layer_ind]
+
+
+class SimpleBlock(nn.Module):
+    """blocks.py:507-561: KPConv(in, out/2) + BN + LeakyReLU."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, layer_ind, config, ops):
+        super().__init__()
+        extent = radius * config.KP_extent / config.conv_radius
+        self.block_name, self.layer_ind = block_name, layer_ind
+        self.KPConv = ops.KPConv(config.num_kernel_points, config.in_points_dim, in_dim, out_dim // 2, extent, radius,
+                                 fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
+                                 aggregation_mode=config.aggregation_mode)
+        self.batch_norm = BatchNormBlock(out_dim // 2, config.use_batch_norm, config.batch_norm_momentum)
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def forward(self, x, batch):
+        q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
+        return self.leaky_relu(self.batch_norm(self.KPConv(q, s, inds, x)))
+
+
+class ResnetBottleneckBlock(nn.Module):
+    """blocks.py:564-649: unary down -> KPConv(d/4, d/4) -> unary up, (max-pooled) shortcut."""
+
+    def __init__(self, block_name, in_dim, out_dim, radius, layer_ind, config, ops):
+        super().__init__()
+        extent = radius * config.KP_extent / config.conv_radius
+        bn, mom = config.use_batch_norm, config.batch_norm_momentum
+        self.block_name, self.layer_ind, self.ops = block_name, layer_ind, ops
+        self.unary1 = UnaryBlock(in_dim, out_dim // 4, bn, mom) if in_dim != out_dim // 4 else nn.Identity()
+        self.KPConv = ops.KPConv(config.num_kernel_points, config.in_points_dim, out_dim // 4, out_dim // 4, extent,
+                                 radius, fixed_kernel_points=config.fixed_kernel_points,
+                                 KP_influence=config.KP_influence, aggregation_mode=config.aggregation_mode)
+        self.batch_norm_conv = BatchNormBlock(out_dim // 4, bn, mom)
+        self.unary2 = UnaryBlock(out_dim // 4, out_dim, bn, mom, no_relu=True)
+        self.unary_shortcut = UnaryBlock(in_dim, out_dim, bn, mom, no_relu=True) if in_dim != out_dim else nn.Identity()
+        self.leaky_relu = nn.LeakyReLU(0.1)
+
+    def forward(self, features, batch):
+        q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
+        x = self.unary1(features)
+        x = self.leaky_relu(self.batch_norm_conv(self.KPConv(q, s, inds, x)))
+        x = self.unary2(x)
+        shortcut = self.ops.max_pool(features, inds) if 'strided' in self.block_name else features
+        return self.leaky_relu(x + self.unary_shortcut(shortcut))
+
+
+class NearestUpsampleBlock(nn.Module):
+    """blocks.py:668-683."""
+
+    def __init__(self, layer_ind, ops):
+        super().__init__()
+        self.layer_ind, self.ops = layer_ind, ops
+
+    def forward(self, x, batch):
+        return self.ops.closest_pool(x, batch.upsamples[self.layer_ind - 1])
+
+
+def _block(name, radius, in_dim, out_dim, layer, config, ops):
+    if name == 'unary':
+        return UnaryBlock(in_dim, out_dim, config.use_batch_norm, config.batch_norm_momentum)
+    if name.startswith('simple'):
+        return SimpleBlock(name, in_dim, out_dim, radius, layer, config, ops)
+    if name.startswith('resnetb'):
+        return ResnetBottleneckBlock(name, in_dim, out_dim, radius, layer, config, ops)
+    if name == 'nearest_upsample':
+        return NearestUpsampleBlock(layer, ops)
+    raise ValueError('Unknown block name in the architecture definition : ' + name)
+
+
+class KPFCNN(nn.Module):
+    """Encoder-decoder segmentation net with the bookkeeping of architectures.py:189-297
+    (radius doubles and feature width doubles at every strided block; skip links are taken before
+    each strided block and concatenated after each upsampling)."""
+
+    def __init__(self, config, num_classes=None, ops=None):
+        super().__init__()
+        ops = ops or product_ops()
+        arch = config.architecture
+        layer, r = 0, config.first_subsampling_dl * config.conv_radius
+        in_dim, out_dim = config.in_features_dim, config.first_features_dim
+        self.C = num_classes or config.num_classes
+        self.encoder_blocks, self.encoder_skips, skip_dims = nn.ModuleList(), [], []
+        first_up = len(arch)
+        for i, name in enumerate(arch):
+            if any(t in name for t in ('pool', 'strided', 'upsample', 'global')):
+                self.encoder_skips.append(i)
+                skip_dims.append(in_dim)
+            if 'upsample' in name:
+                first_up = i
+                break
+            self.encoder_blocks.append(_block(name, r, in_dim, out_dim, layer, config, ops))
+            in_dim = out_dim // 2 if 'simple' in name else out_dim
+            if 'pool' in name or 'strided' in name:
+                layer, r, out_dim = layer + 1, r * 2, out_dim * 2
+        self.decoder_blocks, self.decoder_concats = nn.ModuleList(), []
+        for j, name in enumerate(arch[first_up:]):
+            if j > 0 and 'upsample' in arch[first_up + j - 1]:
+                in_dim += skip_dims[layer]
+                self.decoder_concats.append(j)
+            self.decoder_blocks.append(_block(name, r, in_dim, out_dim, layer, config, ops))
+            in_dim = out_dim
+            if 'upsample' in name:
+                layer, r, out_dim = layer - 1, r * 0.5, out_dim // 2
+        self.head_mlp = UnaryBlock(out_dim, config.first_features_dim, False, 0)
+        # NB the reference leaves the LeakyReLU on the logits (architectures.py:296-297)
+        self.head_softmax = UnaryBlock(config.first_features_dim, self.C, False, 0)
+        self.criterion = nn.CrossEntropyLoss(ignore_index=-1)
+
+    def forward(self, batch, config=None):
+        x = batch.features.clone().detach()
+        skips = []
+        for i, op in enumerate(self.encoder_blocks):
+            if i in self.encoder_skips:
+                skips.append(x)
+            x = op(x, batch)
+        for j, op in enumerate(self.decoder_blocks):
+            if j in self.decoder_concats:
+                x = torch.cat([x, skips.pop()], dim=1)
+            x = op(x, batch)
+        return self.head_softmax(self.head_mlp(x, batch), batch)
+
+    def loss(self, outputs, labels):
+        return self.criterion(outputs.transpose(0, 1).unsqueeze(0), labels.unsqueeze(0))
+
+    def kpconv_layers(self):
+        return [m for m in self.modules() if type(m).__name__.startswith("KPConv")]

@@ -140,3 +140,27 @@ def knn_pixels(image_xyz_list, image_mask_list, queries, k=3):
         d = ((q[i0:i0 + 256, None, :] - keys[None, :, :]) ** 2).sum(-1)
         out[i0:i0 + 256] = ids[np.argsort(d, axis=1, kind="stable")[:, :k]]
     return out
+
+
+# -------------------------------------------------------------------------------------------------
+# nn.Module wrapper so the harness network can run entirely on the CPU oracle (bench.py's CPU
+# baseline leg).  Same constructor surface as the reference module (blocks.py:145-147).
+# -------------------------------------------------------------------------------------------------
+class KPConvOracle(torch.nn.Module):
+    def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
+                 fixed_kernel_points='center', KP_influence='linear', aggregation_mode='sum',
+                 deformable=False, modulated=False):
+        super().__init__()
+        import math
+        from mvkpconv_b200.kernel_points import load_kernels  # host-side data + RNG mirror only
+        assert not deformable and not modulated
+        self.K, self.KP_extent, self.radius = kernel_size, KP_extent, radius
+        self.KP_influence, self.aggregation_mode = KP_influence, aggregation_mode
+        self.weights = torch.nn.Parameter(torch.zeros((kernel_size, in_channels, out_channels)))
+        torch.nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
+        self.kernel_points = torch.nn.Parameter(
+            torch.tensor(load_kernels(radius, kernel_size, p_dim, fixed_kernel_points)), requires_grad=False)
+
+    def forward(self, q_pts, s_pts, neighb_inds, x):
+        return kpconv_forward(q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent,
+                              self.KP_influence, self.aggregation_mode)
