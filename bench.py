@@ -186,6 +186,11 @@ def run_b200(args):
         return ms, L.mvk_launch_count() - l0, clocks, float(last)
 
     ms, launches, clocks, loss_v = timed(False, args.steps, args.warmup, sample_clocks=True)
+    if args.quick:  # profiling runs (ncu): only the device-resident timed region
+        if rank == 0:
+            print(json.dumps({"quick": True, "ms_per_step": round(ms / args.steps, 3), "points": n_pts,
+                              "gpu_launches": int(launches)}), flush=True)
+        return
     ms_e2e, _, _, _ = timed(True, args.steps, max(1, args.warmup // 2))
 
     # ---------------- per-kernel timing inside a timed region (roofline) ----------------
@@ -381,6 +386,7 @@ def main():
     ap.add_argument("--contraction", default=os.environ.get("MVK_CONTRACTION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timed region only (for ncu runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3
