@@ -326,6 +326,317 @@ pool_bwd(const float* __restrict__ go, int nq, int c, const int* __restrict__ ar
     }
 }
 
+// =================================================================================================
+// Fast paths (KP_influence = 'linear', aggregation = 'sum', K <= 16): the configuration every
+// reference script uses (utils/config.py, train_ScanNet_*.py).  Everything else keeps the generic
+// kernels above.
+//
+// Distances use the expansion d2 = |r|^2 - 2 r.kp + |kp|^2 with per-kernel-point constants staged
+// in shared memory (one LDS.128 per kernel point), sqrt.approx and a multiply by 1/extent: the
+// influence is accurate to a few 1e-7 absolute, far inside the 1e-4 feature tolerance (only the
+// neighbour / voxel INDEX kernels need bit-exact arithmetic).
+// =================================================================================================
+constexpr int KF = 16;  // kernel-point slots of the fast paths
+
+__device__ __forceinline__ float sqrt_approx(float v) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+// c[k] = (-2 kx, -2 ky, -2 kz, |kp|^2); unused slots get a huge constant -> influence < 0.
+__device__ __forceinline__ void stage_kp_constants(const KpArgs& a, float4* s_kc) {
+    if (threadIdx.x < KF) {
+        int k = threadIdx.x;
+        float4 c = make_float4(0.f, 0.f, 0.f, 1e30f);
+        if (k < a.K) {
+            float x = a.kp[3 * k], y = a.kp[3 * k + 1], z = a.kp[3 * k + 2];
+            c = make_float4(-2.f * x, -2.f * y, -2.f * z, x * x + y * y + z * z);
+        }
+        s_kc[k] = c;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float influence_fast(float rx, float ry, float rz, float r2, float4 c, float inv_ext) {
+    float d2 = fmaf(rx, c.x, fmaf(ry, c.y, fmaf(rz, c.z, c.w))) + r2;
+    return fmaf(-sqrt_approx(fmaxf(d2, 0.f)), inv_ext, 1.f);
+}
+
+__device__ __forceinline__ void store4(float* of, __nv_bfloat16* ohi, __nv_bfloat16* olo, size_t off, float4 v) {
+    if (of) {
+        *(float4*)(of + off) = v;
+    } else {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+        __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+        uint2 ph, pl;
+        ph.x = *(unsigned int*)&h0; ph.y = *(unsigned int*)&h1;
+        pl.x = *(unsigned int*)&l0; pl.y = *(unsigned int*)&l1;
+        *(uint2*)(ohi + off) = ph;
+        *(uint2*)(olo + off) = pl;
+    }
+}
+
+// ---- forward, cin % 32 == 0 ----------------------------------------------------------------------
+// One warp per query point.
+//   phase 1  lanes = neighbours: influences of the 16 kernel-point slots; non-zero entries are
+//            ballot-compacted into per-kernel-point lists {support row, weight} in shared memory
+//            (list counters live in registers).
+//   phase 2  the warp splits into 32/G sub-groups of G lanes (G*4 = channels per pass, float4 per
+//            lane); sub-group g walks the list of kernel point kb+g, gathering support rows with
+//            128-bit loads, accumulating in registers; the [K, cin] row of the weighted matrix
+//            leaves as 8-byte bf16 hi / lo stores (or float4).
+template <typename IdxT, int G>
+__global__ void __launch_bounds__(256)
+kp_fwd_fast(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+            __nv_bfloat16* __restrict__ out_lo, int hcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SUB = 32 / G;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float4* s_kc = (float4*)smem_raw;  // [KF]
+    const size_t per_warp = (size_t)KF * hcap * 8 + KF * 4;
+    unsigned char* wbase = smem_raw + KF * 16 + wib * per_warp;
+    int2* lists = (int2*)wbase;                          // [KF][hcap]
+    int* cnt_s = (int*)(wbase + (size_t)KF * hcap * 8);  // [KF]
+    stage_kp_constants(a, s_kc);
+    const float inv_ext = 1.f / a.extent;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const int g = lane / G, lg = lane % G;
+    const int kd = a.K * a.cin;
+
+    for (int i = blockIdx.x * wpb + wib; i < a.nq; i += gridDim.x * wpb) {
+        // ---------------- phase 1 ----------------
+        int cnt[KF];
+#pragma unroll
+        for (int k = 0; k < KF; k++) cnt[k] = 0;
+        const float qx = a.q[3 * i], qy = a.q[3 * i + 1], qz = a.q[3 * i + 2];
+        for (int h0 = 0; h0 < a.h; h0 += 32) {
+            const int h = h0 + lane;
+            int j = a.ns;
+            if (h < a.h) j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
+            const bool real = (unsigned int)j < (unsigned int)a.ns;
+            if (__ballot_sync(0xffffffffu, real) == 0u) continue;
+            float rx = 0.f, ry = 0.f, rz = 0.f;
+            if (real) {
+                rx = __ldg(a.s + 3 * (size_t)j) - qx;
+                ry = __ldg(a.s + 3 * (size_t)j + 1) - qy;
+                rz = __ldg(a.s + 3 * (size_t)j + 2) - qz;
+            }
+            const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+#pragma unroll
+            for (int k = 0; k < KF; k++) {
+                const float w = influence_fast(rx, ry, rz, r2, s_kc[k], inv_ext);
+                const bool nz = real && (w > 0.f);
+                const unsigned int m = __ballot_sync(0xffffffffu, nz);
+                if (nz) lists[k * hcap + cnt[k] + __popc(m & lt_mask)] = make_int2(j, __float_as_int(w));
+                cnt[k] += __popc(m);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < KF; k++)
+            if (lane == k) cnt_s[k] = cnt[k];
+        __syncwarp();
+
+        // ---------------- phase 2 ----------------
+        const size_t row = (size_t)i * a.ld;
+        for (int cb = 0; cb < a.cin; cb += G * 4) {
+            const float* xb = a.x + cb + lg * 4;
+#pragma unroll 1
+            for (int kb = 0; kb < KF; kb += SUB) {
+                const int k = kb + g;
+                const int n = cnt_s[k];
+                const int2* lk = lists + k * hcap;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                int t = 0;
+                for (; t + 2 <= n; t += 2) {
+                    const int2 e0 = lk[t], e1 = lk[t + 1];
+                    const float4 x0 = __ldg((const float4*)(xb + (size_t)e0.x * a.cin));
+                    const float4 x1 = __ldg((const float4*)(xb + (size_t)e1.x * a.cin));
+                    const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e1.y);
+                    acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y);
+                    acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
+                    acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y);
+                    acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
+                }
+                if (t < n) {
+                    const int2 e0 = lk[t];
+                    const float4 x0 = __ldg((const float4*)(xb + (size_t)e0.x * a.cin));
+                    const float w0 = __int_as_float(e0.y);
+                    acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y);
+                    acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
+                }
+                if (k < a.K) store4(out_f32, out_hi, out_lo, row + (size_t)k * a.cin + cb + lg * 4, acc);
+            }
+        }
+        for (int c = kd + lane; c < a.ld; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
+        __syncwarp();
+    }
+}
+
+// ---- forward, cin <= 4 (first layer of every network: 2, 4 input features) -----------------------
+// One THREAD per query point, dense over the kernel points (cin FMAs per (neighbour, kernel point)
+// are cheaper than any sparsity bookkeeping); K*CIN accumulators in registers.
+template <typename IdxT, int CIN>
+__global__ void __launch_bounds__(128)
+kp_fwd_tiny(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+            __nv_bfloat16* __restrict__ out_lo) {
+    __shared__ float4 s_kc[KF];
+    stage_kp_constants(a, s_kc);
+    const float inv_ext = 1.f / a.extent;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nq) return;
+    float acc[KF][CIN];
+#pragma unroll
+    for (int k = 0; k < KF; k++)
+#pragma unroll
+        for (int c = 0; c < CIN; c++) acc[k][c] = 0.f;
+    const float qx = a.q[3 * i], qy = a.q[3 * i + 1], qz = a.q[3 * i + 2];
+    for (int h = 0; h < a.h; h++) {
+        const int j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
+        if ((unsigned int)j >= (unsigned int)a.ns) continue;
+        const float rx = __ldg(a.s + 3 * (size_t)j) - qx;
+        const float ry = __ldg(a.s + 3 * (size_t)j + 1) - qy;
+        const float rz = __ldg(a.s + 3 * (size_t)j + 2) - qz;
+        float xv[CIN];
+#pragma unroll
+        for (int c = 0; c < CIN; c++) xv[c] = __ldg(a.x + (size_t)j * CIN + c);
+        const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+#pragma unroll
+        for (int k = 0; k < KF; k++) {
+            const float w = fmaxf(influence_fast(rx, ry, rz, r2, s_kc[k], inv_ext), 0.f);
+#pragma unroll
+            for (int c = 0; c < CIN; c++) acc[k][c] = fmaf(w, xv[c], acc[k][c]);
+        }
+    }
+    const size_t row = (size_t)i * a.ld;
+    if (out_hi && a.ld == KF * 4) {
+        // the whole 64-column bf16 row (zero padding included) as 8 + 8 128-bit stores
+#pragma unroll
+        for (int v8 = 0; v8 < 8; v8++) {
+            unsigned int ph[4], pl[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                float f[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int col = v8 * 8 + u * 2 + e;  // compile-time
+                    const int k = col / CIN, c = col % CIN;
+                    f[e] = (k < KF) ? ((k < a.K) ? acc[k < KF ? k : 0][c] : 0.f) : 0.f;
+                }
+                __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+                float2 hf = __bfloat1622float2(h);
+                __nv_bfloat162 l = __floats2bfloat162_rn(f[0] - hf.x, f[1] - hf.y);
+                ph[u] = *(unsigned int*)&h;
+                pl[u] = *(unsigned int*)&l;
+            }
+            *(uint4*)(out_hi + row + v8 * 8) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *(uint4*)(out_lo + row + v8 * 8) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < KF; k++)
+#pragma unroll
+        for (int c = 0; c < CIN; c++)
+            if (k < a.K) store_out(out_f32, out_hi, out_lo, row + k * CIN + c, acc[k][c]);
+    for (int c = a.K * CIN; c < a.ld; c++) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
+}
+
+// ---- backward w.r.t. x, cin % 32 == 0 --------------------------------------------------------------
+// One warp per query point.
+//   phase 1  lanes = neighbours; every lane appends its own non-zero {kernel point, weight} entries
+//            to a per-neighbour list (slot-major in shared memory: no cross-lane traffic at all).
+//   phase 2  the [K, cin] gradient row of the weighted matrix is staged in shared memory; sub-group
+//            g combines the entries of neighbour g, g+SUB, ... and issues ONE 128-bit vector
+//            atomic per lane and neighbour into grad_x.
+template <typename IdxT, int G>
+__global__ void __launch_bounds__(256)
+kp_bwd_fast(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx, int hcap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int SUB = 32 / G;
+    constexpr int CW = G * 4;  // channels per pass
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float4* s_kc = (float4*)smem_raw;
+    const size_t per_warp = (size_t)KF * hcap * 8 + (size_t)hcap * 8 + (size_t)KF * CW * 4;
+    unsigned char* wbase = smem_raw + KF * 16 + wib * per_warp;
+    int2* ent = (int2*)wbase;                                       // [KF slots][hcap]
+    int* nent = (int*)(wbase + (size_t)KF * hcap * 8);              // [hcap]
+    int* jrow = nent + hcap;                                        // [hcap]
+    float* tile = (float*)(wbase + (size_t)KF * hcap * 8 + (size_t)hcap * 8);  // [KF][CW]
+    stage_kp_constants(a, s_kc);
+    const float inv_ext = 1.f / a.extent;
+    const int g = lane / G, lg = lane % G;
+
+    for (int i = blockIdx.x * wpb + wib; i < a.nq; i += gridDim.x * wpb) {
+        const float qx = a.q[3 * i], qy = a.q[3 * i + 1], qz = a.q[3 * i + 2];
+        for (int h0 = 0; h0 < a.h; h0 += 32) {
+            const int h = h0 + lane;
+            int j = a.ns;
+            if (h < a.h) j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
+            const bool real = (unsigned int)j < (unsigned int)a.ns;
+            int n = 0;
+            if (__ballot_sync(0xffffffffu, real) != 0u) {
+                float rx = 0.f, ry = 0.f, rz = 0.f;
+                if (real) {
+                    rx = __ldg(a.s + 3 * (size_t)j) - qx;
+                    ry = __ldg(a.s + 3 * (size_t)j + 1) - qy;
+                    rz = __ldg(a.s + 3 * (size_t)j + 2) - qz;
+                }
+                const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+#pragma unroll
+                for (int k = 0; k < KF; k++) {
+                    const float w = influence_fast(rx, ry, rz, r2, s_kc[k], inv_ext);
+                    if (real && w > 0.f) {
+                        ent[n * hcap + h] = make_int2(k, __float_as_int(w));
+                        n++;
+                    }
+                }
+            }
+            if (h < hcap) {
+                nent[h] = n;
+                jrow[h] = j;
+            }
+        }
+        __syncwarp();
+        const size_t row = (size_t)i * a.ld;
+        for (int cb = 0; cb < a.cin; cb += CW) {
+            // stage grad rows [k][cb .. cb+CW) of this point
+            for (int t = lane * 4; t < KF * CW; t += 128) {
+                const int k = t / CW, c = t % CW;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < a.K) v = *(const float4*)(gw + row + (size_t)k * a.cin + cb + c);
+                *(float4*)(tile + t) = v;
+            }
+            __syncwarp();
+            for (int h = g; h < a.h; h += SUB) {
+                const int n = nent[h];
+                if (n == 0) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < n; t++) {
+                    const int2 e = ent[t * hcap + h];
+                    const float w = __int_as_float(e.y);
+                    const float4 v = *(const float4*)(tile + e.x * CW + lg * 4);
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
+                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                }
+                atomicAdd((float4*)(gx + (size_t)jrow[h] * a.cin + cb + lg * 4), acc);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+bool fast_ok(int cin, int num_kp, int influence, int aggregation, int ld) {
+    return influence == 1 && aggregation == 0 && num_kp <= KF && (cin == 32 || cin == 64 || cin % 128 == 0) &&
+           (ld % 4 == 0);
+}
+bool tiny_ok(int cin, int num_kp, int influence, int aggregation) {
+    return influence == 1 && aggregation == 0 && num_kp <= KF && cin <= 4;
+}
+int fast_g(int cin) { return cin == 32 ? 8 : (cin == 64 ? 16 : 32); }
+
 int pick_v(int cin) { return (cin % 128 == 0) ? 4 : ((cin % 64 == 0) ? 2 : 1); }
 
 }  // namespace
@@ -346,6 +657,57 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
     if (nq == 0) return MVK_OK;
     KpArgs a{q_pts, s_pts, neighb_inds, x, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
              influence, aggregation};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tiny_ok(cin, num_kp, influence, aggregation)) {
+        const int threads = 128, blocks_t = (nq + threads - 1) / threads;
+#define LAUNCH_TINY(IDX, C)                                                                          \
+    kp_fwd_tiny<IDX, C><<<blocks_t, threads, 0, st>>>(a, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo)
+#define LAUNCH_TINY_C(IDX)                                                                           \
+    do {                                                                                             \
+        if (cin == 1) LAUNCH_TINY(IDX, 1);                                                           \
+        else if (cin == 2) LAUNCH_TINY(IDX, 2);                                                      \
+        else if (cin == 3) LAUNCH_TINY(IDX, 3);                                                      \
+        else LAUNCH_TINY(IDX, 4);                                                                    \
+    } while (0)
+        if (idx_is_i64) LAUNCH_TINY_C(long long);
+        else LAUNCH_TINY_C(int);
+#undef LAUNCH_TINY_C
+#undef LAUNCH_TINY
+        MVK_LAUNCHED("kp_fwd_tiny");
+        return MVK_OK;
+    }
+    if (fast_ok(cin, num_kp, influence, aggregation, ld)) {
+        const int hc = (h + 3) & ~3;  // keeps the per-warp regions 16-byte aligned
+        const size_t pw = (size_t)KF * hc * 8 + KF * 4;
+        if (KF * 16 + pw <= 200 * 1024) {
+            int wpb_f = (int)((44 * 1024) / pw);
+            wpb_f = wpb_f < 1 ? 1 : (wpb_f > 8 ? 8 : wpb_f);
+            const size_t smem_f = KF * 16 + pw * wpb_f;
+            int blocks_f = (nq + wpb_f - 1) / wpb_f;
+            const int maxb_f = num_sms() * 32;
+            if (blocks_f > maxb_f) blocks_f = maxb_f;
+            const int G = fast_g(cin);
+#define LAUNCH_FAST(IDX, GG)                                                                         \
+    do {                                                                                             \
+        auto kern = kp_fwd_fast<IDX, GG>;                                                            \
+        MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
+        kern<<<blocks_f, wpb_f * 32, smem_f, st>>>(a, out_f32, (__nv_bfloat16*)out_hi,               \
+                                                   (__nv_bfloat16*)out_lo, hc);                      \
+    } while (0)
+            if (idx_is_i64) {
+                if (G == 8) LAUNCH_FAST(long long, 8);
+                else if (G == 16) LAUNCH_FAST(long long, 16);
+                else LAUNCH_FAST(long long, 32);
+            } else {
+                if (G == 8) LAUNCH_FAST(int, 8);
+                else if (G == 16) LAUNCH_FAST(int, 16);
+                else LAUNCH_FAST(int, 32);
+            }
+#undef LAUNCH_FAST
+            MVK_LAUNCHED("kp_fwd_fast");
+            return MVK_OK;
+        }
+    }
     int hcap = (h + 31) / 32 * 32;
     size_t per_warp = (size_t)num_kp * hcap * 8 + KP_MAX * 4;
     if (per_warp + 512 > 200 * 1024) return MVK_ERR_RANGE;
@@ -355,7 +717,6 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
     int blocks = (nq + wpb - 1) / wpb;
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;
-    cudaStream_t st = (cudaStream_t)stream;
     int V = pick_v(cin);
     // vector stores need 16B/8B aligned rows
     if (V == 4 && (ld % 4 != 0)) V = 1;
@@ -393,6 +754,38 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
     if (nq == 0) return MVK_OK;
     KpArgs a{q_pts, s_pts, neighb_inds, nullptr, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
              influence, aggregation};
+    if (fast_ok(cin, num_kp, influence, aggregation, ld)) {
+        const int G = fast_g(cin);
+        const int hc = (h + 3) & ~3;  // keeps the per-warp regions 16-byte aligned
+        const size_t pw = (size_t)KF * hc * 8 + (size_t)hc * 8 + (size_t)KF * G * 4 * 4;
+        if (KF * 16 + pw <= 200 * 1024) {
+            int wpb_f = (int)((44 * 1024) / pw);
+            wpb_f = wpb_f < 1 ? 1 : (wpb_f > 8 ? 8 : wpb_f);
+            const size_t smem_f = KF * 16 + pw * wpb_f;
+            int blocks_f = (nq + wpb_f - 1) / wpb_f;
+            const int maxb_f = num_sms() * 32;
+            if (blocks_f > maxb_f) blocks_f = maxb_f;
+            cudaStream_t st_f = (cudaStream_t)stream;
+#define LAUNCH_FASTB(IDX, GG)                                                                        \
+    do {                                                                                             \
+        auto kern = kp_bwd_fast<IDX, GG>;                                                            \
+        MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
+        kern<<<blocks_f, wpb_f * 32, smem_f, st_f>>>(a, grad_weighted, grad_x, hc);                  \
+    } while (0)
+            if (idx_is_i64) {
+                if (G == 8) LAUNCH_FASTB(long long, 8);
+                else if (G == 16) LAUNCH_FASTB(long long, 16);
+                else LAUNCH_FASTB(long long, 32);
+            } else {
+                if (G == 8) LAUNCH_FASTB(int, 8);
+                else if (G == 16) LAUNCH_FASTB(int, 16);
+                else LAUNCH_FASTB(int, 32);
+            }
+#undef LAUNCH_FASTB
+            MVK_LAUNCHED("kp_bwd_fast");
+            return MVK_OK;
+        }
+    }
     int V = pick_v(cin);
     int hcap = (h + 31) / 32 * 32;
     size_t per_warp = (size_t)num_kp * hcap * 8 + KP_MAX * 4 + (size_t)num_kp * 32 * V * 4;
