@@ -379,44 +379,60 @@ __device__ __forceinline__ void store4(float* of, __nv_bfloat16* ohi, __nv_bfloa
     }
 }
 
-// ---- forward, cin % 32 == 0 ----------------------------------------------------------------------
+// ---- forward, cin in {32, 64, 128 m} ---------------------------------------------------------------
 // One warp per query point.
 //   phase 1  lanes = neighbours: influences of the 16 kernel-point slots; non-zero entries are
-//            ballot-compacted into per-kernel-point lists {support row, weight} in shared memory
-//            (list counters live in registers).
-//   phase 2  the warp splits into 32/G sub-groups of G lanes (G*4 = channels per pass, float4 per
-//            lane); sub-group g walks the list of kernel point kb+g, gathering support rows with
-//            128-bit loads, accumulating in registers; the [K, cin] row of the weighted matrix
-//            leaves as 8-byte bf16 hi / lo stores (or float4).
-template <typename IdxT, int G>
+//            ballot-compacted into per-kernel-point lists {byte offset of the support row, weight}
+//            in shared memory (list counters live in registers).
+//   phase 2  the warp splits into SUB = 32/G sub-groups of G lanes (G*4 = channels per pass, one
+//            float4 per lane); in round r sub-group g walks the list of kernel point r*SUB + g,
+//            four entries per trip (four independent 128-bit gathers in flight), accumulating in
+//            registers; the [K, cin] row of the weighted matrix leaves as 8-byte bf16 hi / lo
+//            stores (or float4).
+template <typename IdxT, int G, int HCAP>
 __global__ void __launch_bounds__(256)
 kp_fwd_fast(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-            __nv_bfloat16* __restrict__ out_lo, int hcap) {
+            __nv_bfloat16* __restrict__ out_lo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SUB = 32 / G;
+    constexpr int CW = G * 4;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    float4* s_kc = (float4*)smem_raw;  // [KF]
-    const size_t per_warp = (size_t)KF * hcap * 8 + KF * 4;
-    unsigned char* wbase = smem_raw + KF * 16 + wib * per_warp;
-    int2* lists = (int2*)wbase;                          // [KF][hcap]
-    int* cnt_s = (int*)(wbase + (size_t)KF * hcap * 8);  // [KF]
+    float4* s_kc = (float4*)smem_raw;                                        // [KF]
+    int2* lists = (int2*)(smem_raw + KF * 16) + (size_t)wib * KF * HCAP;     // [KF][HCAP]
+    // finite weights everywhere: the 4-wide trips of phase 2 read (and ignore) entries past a list's end
+    for (int t = lane; t < KF * HCAP; t += 32) lists[t] = make_int2(0, 0);
     stage_kp_constants(a, s_kc);
     const float inv_ext = 1.f / a.extent;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int g = lane / G, lg = lane % G;
-    const int kd = a.K * a.cin;
+    const int cin = a.cin, H = a.h, ns = a.ns, nq = a.nq;
+    const unsigned int row_bytes = (unsigned int)cin * 4u;
+    const int kd = a.K * cin;
+    const int2* lists_g = lists + g * HCAP;
+    const int stride = gridDim.x * wpb;
 
-    for (int i = blockIdx.x * wpb + wib; i < a.nq; i += gridDim.x * wpb) {
+    int i = blockIdx.x * wpb + wib;
+    int j_next = ns;
+    if (i < nq && lane < H) j_next = load_idx<IdxT>(a.inds, (size_t)i * H + lane);
+    for (; i < nq; i += stride) {
         // ---------------- phase 1 ----------------
         int cnt[KF];
 #pragma unroll
         for (int k = 0; k < KF; k++) cnt[k] = 0;
         const float qx = a.q[3 * i], qy = a.q[3 * i + 1], qz = a.q[3 * i + 2];
-        for (int h0 = 0; h0 < a.h; h0 += 32) {
-            const int h = h0 + lane;
-            int j = a.ns;
-            if (h < a.h) j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
-            const bool real = (unsigned int)j < (unsigned int)a.ns;
+        int j = j_next;
+        {   // prefetch the first index chunk of this warp's next point
+            const int in = i + stride;
+            j_next = ns;
+            if (in < nq && lane < H) j_next = load_idx<IdxT>(a.inds, (size_t)in * H + lane);
+        }
+        for (int h0 = 0; h0 < H; h0 += 32) {
+            if (h0 > 0) {
+                const int h = h0 + lane;
+                j = ns;
+                if (h < H) j = load_idx<IdxT>(a.inds, (size_t)i * H + h);
+            }
+            const bool real = (unsigned int)j < (unsigned int)ns;
             if (__ballot_sync(0xffffffffu, real) == 0u) continue;
             float rx = 0.f, ry = 0.f, rz = 0.f;
             if (real) {
@@ -425,49 +441,52 @@ kp_fwd_fast(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ o
                 rz = __ldg(a.s + 3 * (size_t)j + 2) - qz;
             }
             const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+            const int2 ent = make_int2((int)((unsigned int)j * row_bytes), 0);
 #pragma unroll
             for (int k = 0; k < KF; k++) {
                 const float w = influence_fast(rx, ry, rz, r2, s_kc[k], inv_ext);
                 const bool nz = real && (w > 0.f);
                 const unsigned int m = __ballot_sync(0xffffffffu, nz);
-                if (nz) lists[k * hcap + cnt[k] + __popc(m & lt_mask)] = make_int2(j, __float_as_int(w));
+                if (nz) lists[k * HCAP + cnt[k] + __popc(m & lt_mask)] = make_int2(ent.x, __float_as_int(w));
                 cnt[k] += __popc(m);
             }
         }
-#pragma unroll
-        for (int k = 0; k < KF; k++)
-            if (lane == k) cnt_s[k] = cnt[k];
         __syncwarp();
 
         // ---------------- phase 2 ----------------
         const size_t row = (size_t)i * a.ld;
-        for (int cb = 0; cb < a.cin; cb += G * 4) {
-            const float* xb = a.x + cb + lg * 4;
-#pragma unroll 1
-            for (int kb = 0; kb < KF; kb += SUB) {
-                const int k = kb + g;
-                const int n = cnt_s[k];
-                const int2* lk = lists + k * hcap;
+        for (int cb = 0; cb < cin; cb += CW) {
+            const char* xb = (const char*)(a.x + cb + lg * 4);
+#pragma unroll
+            for (int r = 0; r < KF / SUB; r++) {
+                int n = cnt[r * SUB];
+#pragma unroll
+                for (int u = 1; u < SUB; u++) n = (g == u) ? cnt[r * SUB + u] : n;
+                const int2* lk = lists_g + r * SUB * HCAP;
                 float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                int t = 0;
-                for (; t + 2 <= n; t += 2) {
-                    const int2 e0 = lk[t], e1 = lk[t + 1];
-                    const float4 x0 = __ldg((const float4*)(xb + (size_t)e0.x * a.cin));
-                    const float4 x1 = __ldg((const float4*)(xb + (size_t)e1.x * a.cin));
-                    const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e1.y);
+#pragma unroll 1
+                for (int t = 0; t < n; t += 4) {
+                    const int4 e01 = *(const int4*)(lk + t);
+                    const int4 e23 = *(const int4*)(lk + t + 2);
+                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 x0 = __ldg((const float4*)(xb + (unsigned int)e01.x));
+                    float4 x1 = z, x2 = z, x3 = z;
+                    if (t + 1 < n) x1 = __ldg((const float4*)(xb + (unsigned int)e01.z));
+                    if (t + 2 < n) x2 = __ldg((const float4*)(xb + (unsigned int)e23.x));
+                    if (t + 3 < n) x3 = __ldg((const float4*)(xb + (unsigned int)e23.z));
+                    const float w0 = __int_as_float(e01.y), w1 = __int_as_float(e01.w);
+                    const float w2 = __int_as_float(e23.y), w3 = __int_as_float(e23.w);
                     acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y);
                     acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
                     acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y);
                     acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
+                    acc.x = fmaf(w2, x2.x, acc.x); acc.y = fmaf(w2, x2.y, acc.y);
+                    acc.z = fmaf(w2, x2.z, acc.z); acc.w = fmaf(w2, x2.w, acc.w);
+                    acc.x = fmaf(w3, x3.x, acc.x); acc.y = fmaf(w3, x3.y, acc.y);
+                    acc.z = fmaf(w3, x3.z, acc.z); acc.w = fmaf(w3, x3.w, acc.w);
                 }
-                if (t < n) {
-                    const int2 e0 = lk[t];
-                    const float4 x0 = __ldg((const float4*)(xb + (size_t)e0.x * a.cin));
-                    const float w0 = __int_as_float(e0.y);
-                    acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y);
-                    acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
-                }
-                if (k < a.K) store4(out_f32, out_hi, out_lo, row + (size_t)k * a.cin + cb + lg * 4, acc);
+                const int k = r * SUB + g;
+                if (k < a.K) store4(out_f32, out_hi, out_lo, row + (unsigned int)(k * cin + cb + lg * 4), acc);
             }
         }
         for (int c = kd + lane; c < a.ld; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
@@ -544,38 +563,67 @@ kp_fwd_tiny(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ o
     for (int c = a.K * CIN; c < a.ld; c++) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
 }
 
-// ---- backward w.r.t. x, cin % 32 == 0 --------------------------------------------------------------
+// ---- backward w.r.t. x, cin in {32, 64, 128 m} ---------------------------------------------------------
 // One warp per query point.
 //   phase 1  lanes = neighbours; every lane appends its own non-zero {kernel point, weight} entries
 //            to a per-neighbour list (slot-major in shared memory: no cross-lane traffic at all).
-//   phase 2  the [K, cin] gradient row of the weighted matrix is staged in shared memory; sub-group
-//            g combines the entries of neighbour g, g+SUB, ... and issues ONE 128-bit vector
-//            atomic per lane and neighbour into grad_x.
-template <typename IdxT, int G>
+//            Meanwhile the [K, cin] gradient row of the weighted matrix streams into shared memory
+//            with cp.async.
+//   phase 2  sub-group g combines the entries of neighbours g, g+SUB, ... and issues ONE 128-bit
+//            vector atomic per lane and neighbour into grad_x.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <typename IdxT, int G, int HCAP>
 __global__ void __launch_bounds__(256)
-kp_bwd_fast(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx, int hcap) {
+kp_bwd_fast(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SUB = 32 / G;
     constexpr int CW = G * 4;  // channels per pass
+    constexpr size_t PER_WARP = (size_t)KF * HCAP * 8 + (size_t)HCAP * 8 + (size_t)KF * CW * 4;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     float4* s_kc = (float4*)smem_raw;
-    const size_t per_warp = (size_t)KF * hcap * 8 + (size_t)hcap * 8 + (size_t)KF * CW * 4;
-    unsigned char* wbase = smem_raw + KF * 16 + wib * per_warp;
-    int2* ent = (int2*)wbase;                                       // [KF slots][hcap]
-    int* nent = (int*)(wbase + (size_t)KF * hcap * 8);              // [hcap]
-    int* jrow = nent + hcap;                                        // [hcap]
-    float* tile = (float*)(wbase + (size_t)KF * hcap * 8 + (size_t)hcap * 8);  // [KF][CW]
+    unsigned char* wbase = smem_raw + KF * 16 + wib * PER_WARP;
+    int2* ent = (int2*)wbase;                                       // [KF slots][HCAP] {tile byte offset, weight}
+    int2* meta = (int2*)(wbase + (size_t)KF * HCAP * 8);            // [HCAP] {entries, byte offset of the grad_x row}
+    float* tile = (float*)(wbase + (size_t)KF * HCAP * 8 + (size_t)HCAP * 8);  // [KF][CW]
+    for (int t = lane; t < KF * HCAP; t += 32) ent[t] = make_int2(0, 0);
     stage_kp_constants(a, s_kc);
     const float inv_ext = 1.f / a.extent;
     const int g = lane / G, lg = lane % G;
+    const int cin = a.cin, H = a.h, ns = a.ns, nq = a.nq;
+    const unsigned int row_bytes = (unsigned int)cin * 4u;
+    const int kd = a.K * cin;
+    const int stride = gridDim.x * wpb;
+    const char* tile_l = (const char*)tile + lg * 16;
 
-    for (int i = blockIdx.x * wpb + wib; i < a.nq; i += gridDim.x * wpb) {
+    int i = blockIdx.x * wpb + wib;
+    int j_next = ns;
+    if (i < nq && lane < H) j_next = load_idx<IdxT>(a.inds, (size_t)i * H + lane);
+    for (; i < nq; i += stride) {
+        const size_t row = (size_t)i * a.ld;
+        // gradient rows of pass 0 -> shared memory, asynchronously (consumed after phase 1)
+        for (int t = lane * 4; t < KF * CW; t += 128) {
+            const int k = t / CW, c = t % CW;
+            if (k < a.K) cp_async16(tile + t, gw + row + (unsigned int)(k * cin + c));
+        }
         const float qx = a.q[3 * i], qy = a.q[3 * i + 1], qz = a.q[3 * i + 2];
-        for (int h0 = 0; h0 < a.h; h0 += 32) {
+        int j = j_next;
+        {
+            const int in = i + stride;
+            j_next = ns;
+            if (in < nq && lane < H) j_next = load_idx<IdxT>(a.inds, (size_t)in * H + lane);
+        }
+        for (int h0 = 0; h0 < H; h0 += 32) {
             const int h = h0 + lane;
-            int j = a.ns;
-            if (h < a.h) j = load_idx<IdxT>(a.inds, (size_t)i * a.h + h);
-            const bool real = (unsigned int)j < (unsigned int)a.ns;
+            if (h0 > 0) {
+                j = ns;
+                if (h < H) j = load_idx<IdxT>(a.inds, (size_t)i * H + h);
+            }
+            const bool real = (unsigned int)j < (unsigned int)ns;
             int n = 0;
             if (__ballot_sync(0xffffffffu, real) != 0u) {
                 float rx = 0.f, ry = 0.f, rz = 0.f;
@@ -589,43 +637,50 @@ kp_bwd_fast(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx, int 
                 for (int k = 0; k < KF; k++) {
                     const float w = influence_fast(rx, ry, rz, r2, s_kc[k], inv_ext);
                     if (real && w > 0.f) {
-                        ent[n * hcap + h] = make_int2(k, __float_as_int(w));
+                        ent[n * HCAP + h] = make_int2(k * CW * 4, __float_as_int(w));
                         n++;
                     }
                 }
             }
-            if (h < hcap) {
-                nent[h] = n;
-                jrow[h] = j;
+            if (h < HCAP) meta[h] = make_int2(n, (int)((unsigned int)j * row_bytes));
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        for (int cb = 0; cb < cin; cb += CW) {
+            if (cb > 0) {
+                __syncwarp();
+                for (int t = lane * 4; t < KF * CW; t += 128) {
+                    const int k = t / CW, c = t % CW;
+                    if (k < a.K) cp_async16(tile + t, gw + row + (unsigned int)(k * cin + cb + c));
+                }
+                cp_async_wait_all();
+                __syncwarp();
+            }
+            char* gxb = (char*)(gx + cb + lg * 4);
+            for (int h = g; h < H; h += SUB) {
+                const int2 m = meta[h];
+                const int n = m.x;
+                if (n == 0) continue;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+                for (int t = 0; t < n; t += 2) {
+                    const int2 e0 = ent[t * HCAP + h];
+                    const int2 e1 = ent[(t + 1) * HCAP + h];
+                    const float w0 = __int_as_float(e0.y);
+                    const float w1 = (t + 1 < n) ? __int_as_float(e1.y) : 0.f;
+                    const float4 v0 = *(const float4*)(tile_l + e0.x);
+                    const float4 v1 = *(const float4*)(tile_l + e1.x);
+                    acc.x = fmaf(w0, v0.x, acc.x); acc.y = fmaf(w0, v0.y, acc.y);
+                    acc.z = fmaf(w0, v0.z, acc.z); acc.w = fmaf(w0, v0.w, acc.w);
+                    acc.x = fmaf(w1, v1.x, acc.x); acc.y = fmaf(w1, v1.y, acc.y);
+                    acc.z = fmaf(w1, v1.z, acc.z); acc.w = fmaf(w1, v1.w, acc.w);
+                }
+                atomicAdd((float4*)(gxb + (unsigned int)m.y), acc);
             }
         }
         __syncwarp();
-        const size_t row = (size_t)i * a.ld;
-        for (int cb = 0; cb < a.cin; cb += CW) {
-            // stage grad rows [k][cb .. cb+CW) of this point
-            for (int t = lane * 4; t < KF * CW; t += 128) {
-                const int k = t / CW, c = t % CW;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (k < a.K) v = *(const float4*)(gw + row + (size_t)k * a.cin + cb + c);
-                *(float4*)(tile + t) = v;
-            }
-            __syncwarp();
-            for (int h = g; h < a.h; h += SUB) {
-                const int n = nent[h];
-                if (n == 0) continue;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int t = 0; t < n; t++) {
-                    const int2 e = ent[t * hcap + h];
-                    const float w = __int_as_float(e.y);
-                    const float4 v = *(const float4*)(tile + e.x * CW + lg * 4);
-                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-                    acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-                }
-                atomicAdd((float4*)(gx + (size_t)jrow[h] * a.cin + cb + lg * 4), acc);
-            }
-            __syncwarp();
-        }
     }
+    (void)kd;
 }
 
 bool fast_ok(int cin, int num_kp, int influence, int aggregation, int ld) {
@@ -676,37 +731,41 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
         MVK_LAUNCHED("kp_fwd_tiny");
         return MVK_OK;
     }
-    if (fast_ok(cin, num_kp, influence, aggregation, ld)) {
-        const int hc = (h + 3) & ~3;  // keeps the per-warp regions 16-byte aligned
-        const size_t pw = (size_t)KF * hc * 8 + KF * 4;
-        if (KF * 16 + pw <= 200 * 1024) {
-            int wpb_f = (int)((44 * 1024) / pw);
-            wpb_f = wpb_f < 1 ? 1 : (wpb_f > 8 ? 8 : wpb_f);
-            const size_t smem_f = KF * 16 + pw * wpb_f;
-            int blocks_f = (nq + wpb_f - 1) / wpb_f;
-            const int maxb_f = num_sms() * 32;
-            if (blocks_f > maxb_f) blocks_f = maxb_f;
-            const int G = fast_g(cin);
-#define LAUNCH_FAST(IDX, GG)                                                                         \
+    if (fast_ok(cin, num_kp, influence, aggregation, ld) && h <= 64 && (size_t)(ns + 1) * cin * 4 < 0xffffffffull &&
+        (size_t)ld < 0x7fffffffull) {
+        const int HC = h <= 48 ? 48 : 64;
+        const size_t pw = (size_t)KF * HC * 8;
+        int wpb_f = (int)((44 * 1024) / pw);
+        wpb_f = wpb_f > 8 ? 8 : wpb_f;
+        const size_t smem_f = KF * 16 + pw * wpb_f;
+        int blocks_f = (nq + wpb_f - 1) / wpb_f;
+        const int maxb_f = num_sms() * 32;
+        if (blocks_f > maxb_f) blocks_f = maxb_f;
+        const int G = fast_g(cin);
+#define LAUNCH_FAST(IDX, GG, HH)                                                                     \
     do {                                                                                             \
-        auto kern = kp_fwd_fast<IDX, GG>;                                                            \
+        auto kern = kp_fwd_fast<IDX, GG, HH>;                                                        \
         MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
         kern<<<blocks_f, wpb_f * 32, smem_f, st>>>(a, out_f32, (__nv_bfloat16*)out_hi,               \
-                                                   (__nv_bfloat16*)out_lo, hc);                      \
+                                                   (__nv_bfloat16*)out_lo);                          \
     } while (0)
-            if (idx_is_i64) {
-                if (G == 8) LAUNCH_FAST(long long, 8);
-                else if (G == 16) LAUNCH_FAST(long long, 16);
-                else LAUNCH_FAST(long long, 32);
-            } else {
-                if (G == 8) LAUNCH_FAST(int, 8);
-                else if (G == 16) LAUNCH_FAST(int, 16);
-                else LAUNCH_FAST(int, 32);
-            }
-#undef LAUNCH_FAST
-            MVK_LAUNCHED("kp_fwd_fast");
-            return MVK_OK;
+#define LAUNCH_FAST_G(IDX, HH)                                                                       \
+    do {                                                                                             \
+        if (G == 8) LAUNCH_FAST(IDX, 8, HH);                                                         \
+        else if (G == 16) LAUNCH_FAST(IDX, 16, HH);                                                  \
+        else LAUNCH_FAST(IDX, 32, HH);                                                               \
+    } while (0)
+        if (idx_is_i64) {
+            if (HC == 48) LAUNCH_FAST_G(long long, 48);
+            else LAUNCH_FAST_G(long long, 64);
+        } else {
+            if (HC == 48) LAUNCH_FAST_G(int, 48);
+            else LAUNCH_FAST_G(int, 64);
         }
+#undef LAUNCH_FAST_G
+#undef LAUNCH_FAST
+        MVK_LAUNCHED("kp_fwd_fast");
+        return MVK_OK;
     }
     int hcap = (h + 31) / 32 * 32;
     size_t per_warp = (size_t)num_kp * hcap * 8 + KP_MAX * 4;
@@ -754,37 +813,41 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
     if (nq == 0) return MVK_OK;
     KpArgs a{q_pts, s_pts, neighb_inds, nullptr, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
              influence, aggregation};
-    if (fast_ok(cin, num_kp, influence, aggregation, ld)) {
+    if (fast_ok(cin, num_kp, influence, aggregation, ld) && h <= 64 && (size_t)(ns + 1) * cin * 4 < 0xffffffffull &&
+        (size_t)ld < 0x7fffffffull) {
         const int G = fast_g(cin);
-        const int hc = (h + 3) & ~3;  // keeps the per-warp regions 16-byte aligned
-        const size_t pw = (size_t)KF * hc * 8 + (size_t)hc * 8 + (size_t)KF * G * 4 * 4;
-        if (KF * 16 + pw <= 200 * 1024) {
-            int wpb_f = (int)((44 * 1024) / pw);
-            wpb_f = wpb_f < 1 ? 1 : (wpb_f > 8 ? 8 : wpb_f);
-            const size_t smem_f = KF * 16 + pw * wpb_f;
-            int blocks_f = (nq + wpb_f - 1) / wpb_f;
-            const int maxb_f = num_sms() * 32;
-            if (blocks_f > maxb_f) blocks_f = maxb_f;
-            cudaStream_t st_f = (cudaStream_t)stream;
-#define LAUNCH_FASTB(IDX, GG)                                                                        \
+        const int HC = h <= 48 ? 48 : 64;
+        const size_t pw = (size_t)KF * HC * 8 + (size_t)HC * 8 + (size_t)KF * G * 4 * 4;
+        int wpb_f = (int)((44 * 1024) / pw);
+        wpb_f = wpb_f < 1 ? 1 : (wpb_f > 8 ? 8 : wpb_f);
+        const size_t smem_f = KF * 16 + pw * wpb_f;
+        int blocks_f = (nq + wpb_f - 1) / wpb_f;
+        const int maxb_f = num_sms() * 32;
+        if (blocks_f > maxb_f) blocks_f = maxb_f;
+        cudaStream_t st_f = (cudaStream_t)stream;
+#define LAUNCH_FASTB(IDX, GG, HH)                                                                    \
     do {                                                                                             \
-        auto kern = kp_bwd_fast<IDX, GG>;                                                            \
+        auto kern = kp_bwd_fast<IDX, GG, HH>;                                                        \
         MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-        kern<<<blocks_f, wpb_f * 32, smem_f, st_f>>>(a, grad_weighted, grad_x, hc);                  \
+        kern<<<blocks_f, wpb_f * 32, smem_f, st_f>>>(a, grad_weighted, grad_x);                      \
     } while (0)
-            if (idx_is_i64) {
-                if (G == 8) LAUNCH_FASTB(long long, 8);
-                else if (G == 16) LAUNCH_FASTB(long long, 16);
-                else LAUNCH_FASTB(long long, 32);
-            } else {
-                if (G == 8) LAUNCH_FASTB(int, 8);
-                else if (G == 16) LAUNCH_FASTB(int, 16);
-                else LAUNCH_FASTB(int, 32);
-            }
-#undef LAUNCH_FASTB
-            MVK_LAUNCHED("kp_bwd_fast");
-            return MVK_OK;
+#define LAUNCH_FASTB_G(IDX, HH)                                                                      \
+    do {                                                                                             \
+        if (G == 8) LAUNCH_FASTB(IDX, 8, HH);                                                        \
+        else if (G == 16) LAUNCH_FASTB(IDX, 16, HH);                                                 \
+        else LAUNCH_FASTB(IDX, 32, HH);                                                              \
+    } while (0)
+        if (idx_is_i64) {
+            if (HC == 48) LAUNCH_FASTB_G(long long, 48);
+            else LAUNCH_FASTB_G(long long, 64);
+        } else {
+            if (HC == 48) LAUNCH_FASTB_G(int, 48);
+            else LAUNCH_FASTB_G(int, 64);
         }
+#undef LAUNCH_FASTB_G
+#undef LAUNCH_FASTB
+        MVK_LAUNCHED("kp_bwd_fast");
+        return MVK_OK;
     }
     int V = pick_v(cin);
     int hcap = (h + 31) / 32 * 32;
