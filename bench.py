@@ -221,6 +221,14 @@ def run_b200(args):
             M, N, K, terms = a[8], a[9], a[10], a[14]
             key += f"[{'x'.join(map(str, (N, K)))}]"
             work = 2.0 * M * N * K * terms
+        if name in ("mvk_col_stats", "mvk_scale_shift_act"):
+            key += f"[{a[1]}x{a[2]}]"
+        elif name in ("mvk_act_bwd_reduce", "mvk_act_bwd_apply"):
+            key += f"[{a[3]}x{a[4]}]"
+        elif name == "mvk_split_bf16":
+            key += f"[{a[1]}x{a[2]}]"
+        elif name == "mvk_gemm_bf16x3":
+            key = f"mvk_gemm_bf16x3[M={a[8]},N={a[9]},K={a[10]},amn={a[2]},bmn={a[6]},split={a[15]}]"
         r = agg.setdefault(key, [0.0, 0, 0.0, name])
         r[0] += d
         r[1] += 1
@@ -281,6 +289,9 @@ def run_b200(args):
             "neighbor_queries_per_step": int(queries_per_step[0]),
             "breakdown_ms": breakdown, "loss": loss_v,
         }
+        if args.detail:
+            det = sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.detail]
+            line["detail_us_per_call"] = {k: [round(1e3 * v[0] / v[1], 1), v[1] // args.steps] for k, v in det}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(steps=2, warmup=1, seed=0)
         print(json.dumps(line), flush=True)
@@ -386,6 +397,7 @@ def main():
     ap.add_argument("--contraction", default=os.environ.get("MVK_CONTRACTION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", type=int, default=0, help="add the N most expensive (entry point, shape) rows")
     ap.add_argument("--quick", action="store_true", help="device-resident timed region only (for ncu runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

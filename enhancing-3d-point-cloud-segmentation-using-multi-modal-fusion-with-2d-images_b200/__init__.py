@@ -4,6 +4,7 @@ Drop-in operator surface of the reference (dcy0577/Enhancing-3D-Point-Cloud-Segm
 Multi-Modal-Fusion-with-2D-Images) for that path only:
 
     KPConv                     models/blocks.py:143-379         (rigid kernel point convolution)
+    UnaryBlock, BatchNormBlock models/blocks.py:430-504         (+ bn_act: fused bn/residual/LeakyReLU)
     max_pool, closest_pool     models/blocks.py:79-110
     batch_neighbors            datasets/common.py:185-196       (cpp_wrappers/cpp_neighbors)
     grid_subsampling           datasets/common.py:44-74         (cpp_wrappers/cpp_subsampling)
@@ -22,11 +23,12 @@ the directory name mandated for the package is not a valid Python identifier.
 from . import _lib, build  # noqa: F401
 from .geometry import batch_grid_subsampling, batch_neighbors, create_3D_rotations, grid_subsampling  # noqa: F401
 from .kernel_points import load_kernels  # noqa: F401
+from .blocks import BatchNormBlock, UnaryBlock, bn_act  # noqa: F401
 from .kpconv import KPConv, closest_pool, gather, max_pool  # noqa: F401
 from .lifting import FeatureAggregation, depth2xyz, group_points, knn_pixels, unproject_views  # noqa: F401
 
 __all__ = [
-    "KPConv", "max_pool", "closest_pool", "gather", "batch_neighbors", "grid_subsampling",
+    "KPConv", "UnaryBlock", "BatchNormBlock", "bn_act", "max_pool", "closest_pool", "gather", "batch_neighbors", "grid_subsampling",
     "batch_grid_subsampling", "group_points", "FeatureAggregation", "depth2xyz", "unproject_views",
     "knn_pixels", "load_kernels", "create_3D_rotations",
 ]

@@ -25,15 +25,16 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 3;
-constexpr int TILE_BYTES = 16384;              // 128 rows x 128 B
-constexpr int STAGE_BYTES = 4 * TILE_BYTES;    // A_hi | A_lo | B_hi | B_lo
+constexpr int MAX_STAGES = 8;
+constexpr int A_TILE_BYTES = 16384;            // 128 rows x 128 B (one of hi / lo)
 constexpr int NUM_THREADS = 192;
-constexpr int TMEM_COLS = 128;
+constexpr int STAGING_BYTES = 4 * 2 * 4096;    // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
 struct GemmParams {
     float* D;
-    int M, ldd, n_valid, bn, kb_total, kb_per_split, terms, a_mn, b_mn, atomic_out;
+    int M, N, ldd, bn, kb_total, kb_per_split, splits, terms, a_mn, b_mn, atomic_out, stages, tma_store;
+    int m_tiles, n_tiles, num_tiles, tmem_cols, stage_bytes;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -44,6 +45,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
@@ -63,6 +67,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, int reduce_add) {
+    if (reduce_add)
+        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, int mn_major) {
     // SmemDescriptor (cute/arch/mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -97,40 +109,47 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Persistent, warp-specialised: every CTA (one per SM) walks the tile list t = blockIdx.x,
+// blockIdx.x + gridDim.x, ...; tile -> (split, m, n) with n fastest so that the CTAs working on
+// one row block share its A tile through L2.  The smem ring and the two TMEM accumulator buffers
+// run across tile boundaries, so the loads / MMAs of tile i+1 overlap the epilogue of tile i.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-               GemmParams p) {
+               const __grid_constant__ CUtensorMap tm_d, GemmParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[2 * MAX_STAGES + 4];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;  // SW128 tiles need 1 KB alignment
+    const uint32_t staging = smem_base + (uint32_t)p.stages * (uint32_t)p.stage_bytes;
     const uint32_t bar_full = smem_u32(&bars[0]);
-    const uint32_t bar_empty = smem_u32(&bars[STAGES]);
-    const uint32_t bar_tmem = smem_u32(&bars[2 * STAGES]);
-
-    const int m0 = blockIdx.x * BM;
-    const int n0 = blockIdx.y * p.bn;
-    const int kb0 = blockIdx.z * p.kb_per_split;
-    const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+    const uint32_t bar_empty = smem_u32(&bars[MAX_STAGES]);
+    const uint32_t bar_tfull = smem_u32(&bars[2 * MAX_STAGES]);       // [2] accumulator ready
+    const uint32_t bar_tempty = smem_u32(&bars[2 * MAX_STAGES + 2]);  // [2] accumulator drained
+    const int nstages = p.stages;
+    const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
-        for (int s = 0; s < STAGES; s++) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_d) : "memory");
+        for (int s = 0; s < nstages; s++) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_tmem, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_base_smem)), "r"((uint32_t)TMEM_COLS) : "memory");
+                         smem_u32(&tmem_base_smem)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -141,37 +160,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t a_bytes = TILE_BYTES;
-            const uint32_t b_bytes = (uint32_t)p.bn * 128u;
-            const uint32_t stage_tx = (a_bytes + b_bytes) * (p.terms == 3 ? 2u : 1u);
+            const uint32_t stage_tx = (A_TILE_BYTES + b_tile_bytes) * (p.terms == 3 ? 2u : 1u);
             int s = 0;
             uint32_t ph = 0;
-            for (int kb = kb0; kb < kb1; kb++) {
-                mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-                const uint32_t full = bar_full + 8 * s;
-                mbar_expect_tx(full, stage_tx);
-                const uint32_t st = smem_base + s * STAGE_BYTES;
-                const int k0 = kb * BK;
-                for (int half = 0; half < (p.terms == 3 ? 2 : 1); half++) {
-                    const CUtensorMap* ma = half ? &tm_a_lo : &tm_a_hi;
-                    const CUtensorMap* mb = half ? &tm_b_lo : &tm_b_hi;
-                    const uint32_t sa = st + half * TILE_BYTES;
-                    const uint32_t sb = st + (2 + half) * TILE_BYTES;
-                    if (!p.a_mn) {
-                        tma_load_2d(sa, ma, full, k0, m0);
-                    } else {
-                        tma_load_2d(sa, ma, full, m0, k0);
-                        tma_load_2d(sa + 8192, ma, full, m0 + 64, k0);
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+                const int nt = t % p.n_tiles, rest = t / p.n_tiles;
+                const int mt = rest % p.m_tiles, sp = rest / p.m_tiles;
+                const int m0 = mt * BM, n0 = nt * p.bn;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    const uint32_t full = bar_full + 8 * s;
+                    mbar_expect_tx(full, stage_tx);
+                    const uint32_t st = smem_base + s * p.stage_bytes;
+                    const int k0 = kb * BK;
+                    for (int half = 0; half < (p.terms == 3 ? 2 : 1); half++) {
+                        const CUtensorMap* ma = half ? &tm_a_lo : &tm_a_hi;
+                        const CUtensorMap* mb = half ? &tm_b_lo : &tm_b_hi;
+                        const uint32_t sa = st + half * A_TILE_BYTES;
+                        const uint32_t sb = st + 2 * A_TILE_BYTES + half * b_tile_bytes;
+                        if (!p.a_mn) {
+                            tma_load_2d(sa, ma, full, k0, m0);
+                        } else {
+                            tma_load_2d(sa, ma, full, m0, k0);
+                            tma_load_2d(sa + 8192, ma, full, m0 + 64, k0);
+                        }
+                        if (!p.b_mn) {
+                            tma_load_2d(sb, mb, full, k0, n0);
+                        } else {
+                            for (int c = 0; c < p.bn / 64; c++) tma_load_2d(sb + 8192 * c, mb, full, n0 + 64 * c, k0);
+                        }
                     }
-                    if (!p.b_mn) {
-                        tma_load_2d(sb, mb, full, k0, n0);
-                    } else {
-                        for (int c = 0; c < p.bn / 64; c++) tma_load_2d(sb + 8192 * c, mb, full, n0 + 64 * c, k0);
+                    if (++s == nstages) {
+                        s = 0;
+                        ph ^= 1u;
                     }
-                }
-                if (++s == STAGES) {
-                    s = 0;
-                    ph ^= 1u;
                 }
             }
         }
@@ -187,59 +210,99 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
             int s = 0;
             uint32_t ph = 0;
-            uint32_t acc = 0;
-            for (int kb = kb0; kb < kb1; kb++) {
-                mbar_wait(bar_full + 8 * s, ph);
+            int it = 0;
+            for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
+                const int sp = (t / p.n_tiles) / p.m_tiles;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                const int buf = it & 1;
+                const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(bar_tempty + 8 * buf, tph ^ 1u);  // epilogue drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = smem_base + s * STAGE_BYTES;
-                for (int term = 0; term < p.terms; term++) {
-                    const uint32_t sa = st + (term == 1 ? TILE_BYTES : 0);
-                    const uint32_t sb = st + (term == 2 ? 3 : 2) * TILE_BYTES;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * p.bn);
+                uint32_t acc = 0;
+                for (int kb = kb0; kb < kb1; kb++) {
+                    mbar_wait(bar_full + 8 * s, ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = smem_base + s * p.stage_bytes;
+                    for (int term = 0; term < p.terms; term++) {
+                        const uint32_t sa = st + (term == 1 ? A_TILE_BYTES : 0);
+                        const uint32_t sb = st + 2 * A_TILE_BYTES + (term == 2 ? b_tile_bytes : 0);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) {
-                        umma_bf16(tmem_base, make_desc(sa + k * a_kstep, p.a_mn),
-                                  make_desc(sb + k * b_kstep, p.b_mn), idesc, acc);
-                        acc = 1;
+                        for (int k = 0; k < BK / 16; k++) {
+                            umma_bf16(tmem_d, make_desc(sa + k * a_kstep, p.a_mn),
+                                      make_desc(sb + k * b_kstep, p.b_mn), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
+                    if (++s == nstages) {
+                        s = 0;
+                        ph ^= 1u;
                     }
                 }
-                umma_commit(bar_empty + 8 * s);  // frees the smem stage when these MMAs retire
-                if (++s == STAGES) {
-                    s = 0;
-                    ph ^= 1u;
-                }
+                umma_commit(bar_tfull + 8 * buf);  // accumulator complete
             }
-            umma_commit(bar_tmem);  // accumulator complete
         }
     } else {
         // ===================== epilogue =====================
-        mbar_wait(bar_tmem, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quarter = warp & 3;  // TMEM lanes [32q, 32q+32) are only visible to warps with id%4 == q
-        const int row = m0 + quarter * 32 + lane;
-        for (int c0 = 0; c0 < p.bn; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            if (row < p.M) {
-                float* dst = p.D + (size_t)row * p.ldd + n0 + c0;
-                const int ncols = min(32, p.n_valid - (n0 + c0));
-                if (p.atomic_out) {
-                    for (int j = 0; j < ncols; j++) atomicAdd(dst + j, __uint_as_float(v[j]));
-                } else if (ncols == 32 && ((((size_t)dst) & 15) == 0)) {
+        const uint32_t my_stage = staging + (uint32_t)(warp - 2) * 8192u;
+        int it = 0;
+        int sbuf = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
+            const int nt = t % p.n_tiles, mt = (t / p.n_tiles) % p.m_tiles;
+            const int m0 = mt * BM, n0 = nt * p.bn;
+            const int buf = it & 1;
+            const uint32_t tph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(bar_tfull + 8 * buf, tph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = m0 + quarter * 32 + lane;
+            const bool rows_live = (m0 + quarter * 32) < p.M;
+            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+                if (n0 + c0 >= p.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.bn + c0), v);
+                if (!rows_live) continue;
+                if (p.tma_store) {
+                    // registers -> 128B-swizzled staging tile [32 rows x 32 cols] -> TMA store (clips at M, N)
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    const uint32_t dst = my_stage + (uint32_t)sbuf * 4096u + (uint32_t)lane * 128u;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *(float4*)(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                } else {
-                    for (int j = 0; j < ncols; j++) dst[j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t addr = dst + (uint32_t)((j ^ (lane & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]),
+                                     "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_d, my_stage + (uint32_t)sbuf * 4096u, n0 + c0, m0 + quarter * 32, p.atomic_out);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    sbuf ^= 1;
+                } else if (row < p.M) {
+                    float* dst = p.D + (size_t)row * p.ldd + n0 + c0;
+                    const int ncols = min(32, p.N - (n0 + c0));
+                    if (p.atomic_out) {
+                        for (int j = 0; j < ncols; j++) atomicAdd(dst + j, __uint_as_float(v[j]));
+                    } else {
+                        for (int j = 0; j < ncols; j++) dst[j] = __uint_as_float(v[j]);
+                    }
                 }
             }
+            // all tcgen05.ld of this accumulator have completed (wait::ld): hand it back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
 
@@ -259,25 +322,43 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D bf16 tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements.
-int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0, uint32_t box1) {
+// 2D tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements of esize bytes.
+int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0, uint32_t box1,
+             int esize = 2) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point unavailable");
         return MVK_ERR_CUDA;
     }
     cuuint64_t dims[2] = {d0, d1};
-    cuuint64_t strides[1] = {ld * 2};
+    cuuint64_t strides[1] = {ld * (uint64_t)esize};
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base,
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled failed (%d)", (int)r);
         return MVK_ERR_CUDA;
     }
     return MVK_OK;
+}
+
+// Widest N tile whose padding waste stays small: wide tiles re-read the A operand least.
+int choose_bn(int N, bool b_mn) {
+    const int cands[4] = {256, 128, 64, 32};
+    int min_pad = 1 << 30;
+    for (int i = 0; i < 4; i++) {
+        if (b_mn && cands[i] < 64) continue;
+        int pad = (N + cands[i] - 1) / cands[i] * cands[i];
+        if (pad < min_pad) min_pad = pad;
+    }
+    for (int i = 0; i < 4; i++) {
+        if (b_mn && cands[i] < 64) continue;
+        int pad = (N + cands[i] - 1) / cands[i] * cands[i];
+        if ((long long)pad * 100 <= (long long)min_pad * 115) return cands[i];
+    }
+    return 64;
 }
 
 }  // namespace
@@ -288,30 +369,38 @@ using namespace mvk;
 extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
                                const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
                                int n_valid, int terms, int split_k, mvk_stream_t stream) {
-    if (!a_hi || !b_hi || !D || M < 1 || N < 64 || K < 1 || (N % 64) != 0 || (lda % 8) != 0 || (ldb % 8) != 0 ||
+    if (!a_hi || !b_hi || !D || M < 1 || N < 1 || K < 1 || (lda % 8) != 0 || (ldb % 8) != 0 ||
         n_valid < 1 || n_valid > N || ldd < n_valid || (terms != 1 && terms != 3))
         return MVK_ERR_INVALID_ARG;
     if (terms == 3 && (!a_lo || !b_lo)) return MVK_ERR_INVALID_ARG;
     if ((((size_t)a_hi | (size_t)b_hi | (size_t)(a_lo ? a_lo : a_hi) | (size_t)(b_lo ? b_lo : b_hi)) & 15) != 0)
         return MVK_ERR_INVALID_ARG;
-    const int bn = (N % 128 == 0) ? 128 : 64;
     GemmParams p;
     p.D = D;
     p.M = M;
+    p.N = n_valid;  // columns past n_valid are neither loaded (zero-filled) nor stored
     p.ldd = ldd;
-    p.n_valid = n_valid;
-    p.bn = bn;
+    p.a_mn = a_mn_major ? 1 : 0;
+    p.b_mn = b_mn_major ? 1 : 0;
+    p.bn = choose_bn(n_valid, p.b_mn != 0);
     p.kb_total = (K + BK - 1) / BK;
     if (split_k < 1) split_k = 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
     p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
-    int splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
     p.terms = terms;
-    p.a_mn = a_mn_major ? 1 : 0;
-    p.b_mn = b_mn_major ? 1 : 0;
-    p.atomic_out = splits > 1 ? 1 : 0;
+    p.atomic_out = p.splits > 1 ? 1 : 0;
+    p.m_tiles = (M + BM - 1) / BM;
+    p.n_tiles = (n_valid + p.bn - 1) / p.bn;
+    p.num_tiles = p.m_tiles * p.n_tiles * p.splits;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
+    p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
+    p.stages = (SMEM_LIMIT - 2048 - STAGING_BYTES) / p.stage_bytes;  // 1 KB alignment slack + static smem
+    if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+    p.tma_store = ((ldd % 4) == 0 && (((size_t)D) & 15) == 0) ? 1 : 0;
 
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, md;
     int rc;
     const void* al = a_lo ? a_lo : a_hi;
     const void* bl = b_lo ? b_lo : b_hi;
@@ -323,16 +412,21 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
         if ((rc = make_map(&ma_lo, al, M, K, lda, 64, 64))) return rc;
     }
     if (!p.b_mn) {
-        if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, 64, bn))) return rc;
-        if ((rc = make_map(&mb_lo, bl, K, N, ldb, 64, bn))) return rc;
+        if ((rc = make_map(&mb_hi, b_hi, K, N, ldb, 64, p.bn))) return rc;
+        if ((rc = make_map(&mb_lo, bl, K, N, ldb, 64, p.bn))) return rc;
     } else {
         if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, 64, 64))) return rc;
         if ((rc = make_map(&mb_lo, bl, N, K, ldb, 64, 64))) return rc;
     }
-    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-    MVK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((M + BM - 1) / BM, N / bn, splits);
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    if (p.tma_store) {
+        if ((rc = make_map(&md, D, n_valid, M, ldd, 32, 32, 4))) return rc;
+    } else {
+        md = ma_hi;  // unused
+    }
+    const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + STAGING_BYTES;
+    MVK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
+    int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+    gemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
     MVK_LAUNCHED("gemm_tc_kernel");
     return MVK_OK;
 }

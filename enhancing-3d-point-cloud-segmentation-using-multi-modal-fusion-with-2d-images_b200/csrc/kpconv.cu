@@ -281,6 +281,26 @@ split_bf16_kernel(const float* __restrict__ src, int rows, int cols, int src_ld,
     }
 }
 
+// dense [rows, 4*cv] case: one float4 in, two 8-byte stores out per thread and trip
+__global__ void __launch_bounds__(256)
+split_bf16_vec4(const float* __restrict__ src, int rows, int cv, int src_ld, __nv_bfloat16* __restrict__ hi,
+                __nv_bfloat16* __restrict__ lo) {
+    const size_t total = (size_t)rows * cv;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cv), c = (int)(t % cv) * 4;
+        const float4 v = *(const float4*)(src + (size_t)r * src_ld + c);
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+        __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+        uint2 ph, pl;
+        ph.x = *(unsigned int*)&h0; ph.y = *(unsigned int*)&h1;
+        pl.x = *(unsigned int*)&l0; pl.y = *(unsigned int*)&l1;
+        *(uint2*)(hi + t * 4) = ph;
+        *(uint2*)(lo + t * 4) = pl;
+    }
+}
+
 // mode 0: max over neighbours with a ZERO shadow row (blocks.py:93-110); mode 1: first column.
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
@@ -886,6 +906,15 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
         return MVK_ERR_INVALID_ARG;
     size_t total = (size_t)rows_pad * ld;
     if (total == 0) return MVK_OK;
+    if (lo && rows_pad == rows && ld == cols && cols % 4 == 0 && src_ld % 4 == 0 && (((size_t)src) & 15) == 0 &&
+        (((size_t)hi | (size_t)lo) & 7) == 0) {
+        const size_t nv = (size_t)rows * (cols / 4);
+        size_t nb = (nv + 255) / 256, mb = (size_t)num_sms() * 16;
+        split_bf16_vec4<<<(int)(nb < mb ? nb : mb), 256, 0, (cudaStream_t)stream>>>(
+            src, rows, cols / 4, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+        MVK_LAUNCHED("split_bf16_vec4");
+        return MVK_OK;
+    }
     int blocks = (int)((total + 255) / 256);
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;

@@ -7,20 +7,32 @@ benchmark configuration ("KPConv baseline encoder-decoder, train_ScanNet_baselin
 driver that exists on the GPU box, where the reference tree is absent.  This harness follows the
 same block grammar ('simple', 'resnetb', 'resnetb_strided', 'nearest_upsample', 'unary') and the
 same dimension / radius bookkeeping, so its KPConv layers have exactly the shapes of SURVEY.md
-Appendix B.  KPConv / max_pool / closest_pool are this package's CUDA ops; the unary blocks
-(Linear + BatchNorm1d + LeakyReLU) are plain library layers.  The operator set is injectable so
-bench.py's CPU baseline can run the identical graph on the oracle's torch-CPU KPConv.
+Appendix B.  KPConv / max_pool / closest_pool and the point-wise blocks (UnaryBlock,
+BatchNormBlock, the fused "batch norm + residual + LeakyReLU" block tail) are this package's CUDA
+ops.  The operator set is injectable so bench.py's CPU baseline can run the identical graph on
+the oracle's torch-CPU KPConv with plain torch layers for the point-wise blocks (the classes
+below), which is exactly what the reference does.
 """
 from types import SimpleNamespace
 
 import torch
 import torch.nn as nn
 
+from . import blocks as _blocks
 from . import kpconv as _kp
 
 
 def product_ops():
-    return SimpleNamespace(KPConv=_kp.KPConv, max_pool=_kp.max_pool, closest_pool=_kp.closest_pool)
+    return SimpleNamespace(KPConv=_kp.KPConv, max_pool=_kp.max_pool, closest_pool=_kp.closest_pool,
+                           UnaryBlock=_blocks.UnaryBlock, BatchNormBlock=_blocks.BatchNormBlock, bn_act=_blocks.bn_act)
+
+
+def _unary(ops, *args, **kw):
+    return getattr(ops, "UnaryBlock", UnaryBlock)(*args, **kw)
+
+
+def _bnblock(ops, *args):
+    return getattr(ops, "BatchNormBlock", BatchNormBlock)(*args)
 
 
 class BatchNormBlock(nn.Module):
@@ -69,12 +81,16 @@ class SimpleBlock(nn.Module):
         self.KPConv = ops.KPConv(config.num_kernel_points, config.in_points_dim, in_dim, out_dim // 2, extent, radius,
                                  fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
                                  aggregation_mode=config.aggregation_mode)
-        self.batch_norm = BatchNormBlock(out_dim // 2, config.use_batch_norm, config.batch_norm_momentum)
+        self.batch_norm = _bnblock(ops, out_dim // 2, config.use_batch_norm, config.batch_norm_momentum)
         self.leaky_relu = nn.LeakyReLU(0.1)
+        self.bn_act = getattr(ops, "bn_act", None)
 
     def forward(self, x, batch):
         q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
-        return self.leaky_relu(self.batch_norm(self.KPConv(q, s, inds, x)))
+        y = self.KPConv(q, s, inds, x)
+        if self.bn_act is not None:
+            return self.bn_act(y, self.batch_norm, slope=0.1)
+        return self.leaky_relu(self.batch_norm(y))
 
 
 class ResnetBottleneckBlock(nn.Module):
@@ -85,21 +101,26 @@ class ResnetBottleneckBlock(nn.Module):
         extent = radius * config.KP_extent / config.conv_radius
         bn, mom = config.use_batch_norm, config.batch_norm_momentum
         self.block_name, self.layer_ind, self.ops = block_name, layer_ind, ops
-        self.unary1 = UnaryBlock(in_dim, out_dim // 4, bn, mom) if in_dim != out_dim // 4 else nn.Identity()
+        self.unary1 = _unary(ops, in_dim, out_dim // 4, bn, mom) if in_dim != out_dim // 4 else nn.Identity()
         self.KPConv = ops.KPConv(config.num_kernel_points, config.in_points_dim, out_dim // 4, out_dim // 4, extent,
                                  radius, fixed_kernel_points=config.fixed_kernel_points,
                                  KP_influence=config.KP_influence, aggregation_mode=config.aggregation_mode)
-        self.batch_norm_conv = BatchNormBlock(out_dim // 4, bn, mom)
-        self.unary2 = UnaryBlock(out_dim // 4, out_dim, bn, mom, no_relu=True)
-        self.unary_shortcut = UnaryBlock(in_dim, out_dim, bn, mom, no_relu=True) if in_dim != out_dim else nn.Identity()
+        self.batch_norm_conv = _bnblock(ops, out_dim // 4, bn, mom)
+        self.unary2 = _unary(ops, out_dim // 4, out_dim, bn, mom, no_relu=True)
+        self.unary_shortcut = _unary(ops, in_dim, out_dim, bn, mom, no_relu=True) if in_dim != out_dim else nn.Identity()
         self.leaky_relu = nn.LeakyReLU(0.1)
+        self.bn_act = getattr(ops, "bn_act", None)
 
     def forward(self, features, batch):
         q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
         x = self.unary1(features)
-        x = self.leaky_relu(self.batch_norm_conv(self.KPConv(q, s, inds, x)))
-        x = self.unary2(x)
+        y = self.KPConv(q, s, inds, x)
         shortcut = self.ops.max_pool(features, inds) if 'strided' in self.block_name else features
+        if self.bn_act is not None:  # product path: fused bn + act, and bn + residual + act tail
+            x = self.bn_act(y, self.batch_norm_conv, slope=0.1)
+            return self.unary2(x, residual=self.unary_shortcut(shortcut), slope=0.1)
+        x = self.leaky_relu(self.batch_norm_conv(y))
+        x = self.unary2(x)
         return self.leaky_relu(x + self.unary_shortcut(shortcut))
 
 
@@ -116,7 +137,7 @@ class NearestUpsampleBlock(nn.Module):
 
 def _block(name, radius, in_dim, out_dim, layer, config, ops):
     if name == 'unary':
-        return UnaryBlock(in_dim, out_dim, config.use_batch_norm, config.batch_norm_momentum)
+        return _unary(ops, in_dim, out_dim, config.use_batch_norm, config.batch_norm_momentum)
     if name.startswith('simple'):
         return SimpleBlock(name, in_dim, out_dim, radius, layer, config, ops)
     if name.startswith('resnetb'):
@@ -160,9 +181,9 @@ class KPFCNN(nn.Module):
             in_dim = out_dim
             if 'upsample' in name:
                 layer, r, out_dim = layer - 1, r * 0.5, out_dim // 2
-        self.head_mlp = UnaryBlock(out_dim, config.first_features_dim, False, 0)
+        self.head_mlp = _unary(ops, out_dim, config.first_features_dim, False, 0)
         # NB the reference leaves the LeakyReLU on the logits (architectures.py:296-297)
-        self.head_softmax = UnaryBlock(config.first_features_dim, self.C, False, 0)
+        self.head_softmax = _unary(ops, config.first_features_dim, self.C, False, 0)
         self.criterion = nn.CrossEntropyLoss(ignore_index=-1)
 
     def forward(self, batch, config=None):

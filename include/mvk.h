@@ -149,8 +149,9 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
  * relative), terms = 1 evaluates hi*hi only (plain bf16).
  *   a_mn_major = 0: A stored [M, lda] (K contiguous);   1: A stored [K, lda] (M contiguous)
  *   b_mn_major = 0: B stored [N, ldb] (K contiguous);   1: B stored [K, ldb] (N contiguous)
- * K must be a multiple of 64 unless the k extent is covered by zero padding up to one (see
- * DESIGN.md); N (operand extent, >= n_valid) a multiple of 64, lda/ldb multiples of 8.
+ * M, N, K are the true extents: tiles that reach past them are zero-filled by TMA (out-of-bounds
+ * fill), so no operand padding is needed; lda/ldb must be multiples of 8 elements (16-byte row
+ * pitch) and the base pointers 16-byte aligned.  n_valid <= N columns of D are written.
  * split_k > 1 partitions K over CTAs and accumulates into D with fp32 atomics (D must be zeroed). */
 int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
                     const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
@@ -160,6 +161,42 @@ int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda,
 int mvk_gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B, long long b_rs,
                  long long b_cs, int M, int N, int K, float* D, int ldd, int split_k,
                  mvk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Point-wise blocks either side of KPConv.
+ * Replaces the ATen chains of BatchNormBlock / UnaryBlock / the ResnetBottleneckBlock tail,
+ * KPConv-PyTorch/models/blocks.py:430-466, :469-504, :637-649:
+ *      UnaryBlock      z = leaky( bn( x W^T ) )          (Linear without bias on mvk_gemm_bf16x3)
+ *      block tail      z = leaky( bn(y) + shortcut )
+ * All matrices are [rows, cols] fp32 row-major with explicit leading dimensions.
+ *
+ * mvk_col_stats       stats[c] += sum_r y[r,c], stats[cols+c] += sum_r y[r,c]^2  (fp64, caller zeroes)
+ * mvk_bn_finalize     training: batch mean / biased variance -> scale = gamma*invstd,
+ *                     shift = beta - mean*scale, running stats updated like torch.nn.BatchNorm1d
+ *                     (momentum, unbiased variance); eval: scale/shift from the running stats.
+ * mvk_scale_shift_act out = leaky(y*scale + shift [+ residual]); scale NULL = 1 (bias-only block);
+ *                     optional bf16 hi/lo copy (the operand format of mvk_gemm_bf16x3).
+ * mvk_act_bwd_reduce  d = dz * leaky'(pre); sums[c] += d, sums[cols+c] += d * xhat   (fp64)
+ * mvk_act_bwd_apply   dy = scale*(d - sum_d/rows - xhat*sum_dxhat/rows)  (batch_stats != 0)
+ *                     dy = scale*d                                         (otherwise)
+ *                     written as fp32 and/or bf16 hi/lo; dres = d (gradient of the residual);
+ *                     dgamma = sums[cols:], dbeta = sums[:cols].
+ * ---------------------------------------------------------------------------------------------- */
+int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk_stream_t stream);
+int mvk_bn_finalize(const double* stats, int rows, int cols, const float* gamma, const float* beta, float eps,
+                    float momentum, int training, float* running_mean, float* running_var, float* scale,
+                    float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream);
+int mvk_scale_shift_act(const float* y, int rows, int cols, int ld, const float* scale, const float* shift,
+                        const float* residual, int ldr, float slope, float* out, int ldo, void* out_hi_bf16,
+                        void* out_lo_bf16, int ldh, mvk_stream_t stream);
+int mvk_act_bwd_reduce(const float* dz, int lddz, const float* y, int rows, int cols, int ld, const float* scale,
+                       const float* shift, const float* residual, int ldr, const float* mean, const float* invstd,
+                       float slope, double* sums, mvk_stream_t stream);
+int mvk_act_bwd_apply(const float* dz, int lddz, const float* y, int rows, int cols, int ld, const float* scale,
+                      const float* shift, const float* residual, int ldr, const float* mean, const float* invstd,
+                      float slope, const double* sums, int batch_stats, float* dy, int lddy, void* dy_hi_bf16,
+                      void* dy_lo_bf16, int ldh, float* dres, int lddres, float* dgamma, float* dbeta,
+                      mvk_stream_t stream);
 
 /* Gather pools on the neighbour matrices (blocks.py:79-110): mode 0 = max_pool (zero-padded
  * shadow row!), 1 = closest_pool (first column).  arg_out [nq, c] i32 (max_pool only) records the

@@ -12,6 +12,7 @@ from the reference file's own AST in memory.
 Versions that produced the committed files are stored inside each .npz under key "_versions".
 """
 import ast
+import zlib
 import os
 import sys
 import types
@@ -244,10 +245,61 @@ def make_geometry():
     print("geometry.npz", sp.shape, conv.shape, pool.shape, up.shape)
 
 
+def make_blocks(blocks):
+    """UnaryBlock / BatchNormBlock of the reference (models/blocks.py:430-504): forward, backward,
+    running statistics, in train and eval mode, with and without batch norm."""
+    flat = {}
+    specs = [
+        # name, rows, cin, cout, use_bn, no_relu, train
+        ("bn_relu_train", 700, 32, 64, True, False, True),
+        ("bn_norelu_train", 513, 64, 128, True, True, True),
+        ("bn_relu_eval", 300, 128, 32, True, False, False),
+        ("bias_relu", 400, 128, 20, False, False, True),
+        ("bias_norelu", 257, 48, 24, False, True, True),
+    ]
+    for name, rows, cin, cout, use_bn, no_relu, train in specs:
+        torch.manual_seed(zlib.crc32(name.encode()) % 1000)
+        blk = blocks.UnaryBlock(cin, cout, use_bn, 0.02, no_relu=no_relu)
+        with torch.no_grad():
+            if use_bn:
+                blk.batch_norm.batch_norm.weight.uniform_(0.5, 1.5)
+                blk.batch_norm.batch_norm.bias.uniform_(-0.5, 0.5)
+                blk.batch_norm.batch_norm.running_mean.uniform_(-0.2, 0.2)
+                blk.batch_norm.batch_norm.running_var.uniform_(0.5, 1.5)
+            else:
+                blk.batch_norm.bias.uniform_(-0.5, 0.5)
+        blk.train(train)
+        x = (torch.randn(rows, cin) * 1.5 + 0.3).requires_grad_(True)
+        go = torch.randn(rows, cout)
+        c = {"x": x.detach().numpy().copy(), "grad_out": go.numpy(), "weight": blk.mlp.weight.detach().numpy().copy(),
+             "use_bn": np.array(use_bn), "no_relu": np.array(no_relu), "train": np.array(train)}
+        if use_bn:
+            bn = blk.batch_norm.batch_norm
+            c.update(gamma=bn.weight.detach().numpy().copy(), beta=bn.bias.detach().numpy().copy(),
+                     rm0=bn.running_mean.numpy().copy(), rv0=bn.running_var.numpy().copy())
+        else:
+            c["bias"] = blk.batch_norm.bias.detach().numpy().copy()
+        out = blk(x)
+        out.backward(go)
+        c.update(out=out.detach().numpy(), grad_x=x.grad.numpy(), grad_w=blk.mlp.weight.grad.numpy())
+        if use_bn:
+            c.update(grad_gamma=bn.weight.grad.numpy(), grad_beta=bn.bias.grad.numpy(), rm1=bn.running_mean.numpy().copy(),
+                     rv1=bn.running_var.numpy().copy(), nbt=np.array(int(bn.num_batches_tracked)))
+        else:
+            c["grad_bias"] = blk.batch_norm.bias.grad.numpy()
+        for k, v in c.items():
+            flat[f"{name}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "blocks.npz"), _versions=_versions(), **flat)
+    print("blocks.npz", len(flat))
+
+
 if __name__ == "__main__":
     only = sys.argv[1:]
     if only == ["fa"]:
         make_feature_aggregation(import_reference_feature_aggregation())
+        sys.exit(0)
+    if only == ["blocks"]:
+        make_blocks(import_reference_kpconv())
         sys.exit(0)
     make_geometry()
     make_lifting()
@@ -255,3 +307,4 @@ if __name__ == "__main__":
     make_feature_aggregation(FA)
     blocks = import_reference_kpconv()
     make_kpconv(blocks)
+    make_blocks(blocks)

@@ -1,0 +1,113 @@
+"""GPU parity of the point-wise blocks (UnaryBlock / BatchNormBlock / fused block tail) against
+golden vectors produced by the reference's own modules (models/blocks.py:430-504) and against
+torch autograd for the fused residual tail.  Tolerance: 1e-4 relative (max-abs / max|ref|) for
+the fp32 and bf16x3 contractions, like KPConv."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    b = b.detach().double().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def build_block(mvk, c, contraction):
+    from mvkpconv_b200 import blocks
+    cout, cin = c["weight"].shape
+    blk = blocks.UnaryBlock(cin, cout, bool(c["use_bn"]), 0.02, no_relu=bool(c["no_relu"]), contraction=contraction).cuda()
+    with torch.no_grad():
+        blk.mlp.weight.copy_(torch.from_numpy(c["weight"]))
+        if bool(c["use_bn"]):
+            bn = blk.batch_norm.batch_norm
+            bn.weight.copy_(torch.from_numpy(c["gamma"]))
+            bn.bias.copy_(torch.from_numpy(c["beta"]))
+            bn.running_mean.copy_(torch.from_numpy(c["rm0"]))
+            bn.running_var.copy_(torch.from_numpy(c["rv0"]))
+        else:
+            blk.batch_norm.bias.copy_(torch.from_numpy(c["bias"]))
+    blk.train(bool(c["train"]))
+    return blk
+
+
+@pytest.mark.parametrize("contraction", ["fp32", "bf16x3"])
+def test_unary_block_vs_reference_golden(mvk, contraction):
+    g = load_golden("blocks")
+    for name, c in g.items():
+        if name.startswith("_"):
+            continue
+        blk = build_block(mvk, c, contraction)
+        x = torch.from_numpy(c["x"]).cuda().requires_grad_(True)
+        out = blk(x)
+        out.backward(torch.from_numpy(c["grad_out"]).cuda())
+        tol = 1e-4
+        assert rel_err(out, c["out"]) < tol, (name, "out")
+        assert rel_err(x.grad, c["grad_x"]) < tol, (name, "grad_x")
+        assert rel_err(blk.mlp.weight.grad, c["grad_w"]) < tol, (name, "grad_w")
+        if bool(c["use_bn"]):
+            bn = blk.batch_norm.batch_norm
+            assert rel_err(bn.weight.grad, c["grad_gamma"]) < tol, (name, "grad_gamma")
+            assert rel_err(bn.bias.grad, c["grad_beta"]) < tol, (name, "grad_beta")
+            assert rel_err(bn.running_mean, c["rm1"]) < 1e-5, (name, "running_mean")
+            assert rel_err(bn.running_var, c["rv1"]) < 1e-5, (name, "running_var")
+            assert int(bn.num_batches_tracked) == int(c["nbt"]), name
+        else:
+            assert rel_err(blk.batch_norm.bias.grad, c["grad_bias"]) < tol, (name, "grad_bias")
+
+
+def test_bn_act_and_residual_tail_vs_torch(mvk):
+    """leaky(bn(y) + shortcut) and leaky(bn(x W^T) + shortcut) against torch autograd (fp32 on the GPU)."""
+    from mvkpconv_b200 import blocks
+    torch.manual_seed(3)
+    rows, cin, cout = 3000, 32, 128
+    x = torch.randn(rows, cin, device="cuda")
+    sc = torch.randn(rows, cout, device="cuda")
+    go = torch.randn(rows, cout, device="cuda")
+    blk = blocks.UnaryBlock(cin, cout, True, 0.02, no_relu=True).cuda()
+    ref_lin = torch.nn.Linear(cin, cout, bias=False).cuda()
+    ref_bn = torch.nn.BatchNorm1d(cout, momentum=0.02).cuda()
+    with torch.no_grad():
+        ref_lin.weight.copy_(blk.mlp.weight)
+        blk.batch_norm.batch_norm.weight.uniform_(0.5, 1.5)
+        blk.batch_norm.batch_norm.bias.uniform_(-0.3, 0.3)
+        ref_bn.weight.copy_(blk.batch_norm.batch_norm.weight)
+        ref_bn.bias.copy_(blk.batch_norm.batch_norm.bias)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    xa, sa = x.clone().requires_grad_(True), sc.clone().requires_grad_(True)
+    xb, sb = x.clone().requires_grad_(True), sc.clone().requires_grad_(True)
+    out = blk(xa, residual=sa, slope=0.1)
+    out.backward(go)
+    ref = torch.nn.functional.leaky_relu(ref_bn(ref_lin(xb)) + sb, 0.1)
+    ref.backward(go)
+    assert rel_err(out, ref) < 1e-4
+    assert rel_err(xa.grad, xb.grad) < 1e-4
+    assert rel_err(sa.grad, sb.grad) < 1e-4
+    assert rel_err(blk.mlp.weight.grad, ref_lin.weight.grad) < 1e-4
+    assert rel_err(blk.batch_norm.batch_norm.weight.grad, ref_bn.weight.grad) < 1e-4
+    assert rel_err(blk.batch_norm.batch_norm.bias.grad, ref_bn.bias.grad) < 1e-4
+    # stand-alone bn + activation (the KPConv -> batch norm -> LeakyReLU step of the blocks)
+    bnb = blocks.BatchNormBlock(cout, True, 0.02).cuda()
+    ref_bn2 = torch.nn.BatchNorm1d(cout, momentum=0.02).cuda()
+    ya, yb = sc.clone().requires_grad_(True), sc.clone().requires_grad_(True)
+    z = blocks.bn_act(ya, bnb, slope=0.1)
+    z.backward(go)
+    zr = torch.nn.functional.leaky_relu(ref_bn2(yb), 0.1)
+    zr.backward(go)
+    assert rel_err(z, zr) < 1e-5
+    assert rel_err(ya.grad, yb.grad) < 1e-4
+    assert rel_err(bnb.batch_norm.running_var, ref_bn2.running_var) < 1e-5
+    # odd column count (num_classes = 19 -> scalar path), bias only
+    bb = blocks.BatchNormBlock(19, False, 0.02).cuda()
+    with torch.no_grad():
+        bb.bias.uniform_(-1, 1)
+    y19 = torch.randn(777, 19, device="cuda", requires_grad=True)
+    z19 = bb(y19)
+    assert rel_err(z19, y19.detach() + bb.bias.detach()) < 1e-6
+    z19.backward(torch.ones_like(z19))
+    assert rel_err(bb.bias.grad, torch.full((19,), 777.0)) < 1e-6
+    assert rel_err(y19.grad, torch.ones_like(y19)) < 1e-6
