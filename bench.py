@@ -203,61 +203,81 @@ def run_b200(args):
         pe1.record()
         torch.cuda.synchronize()
     prof_ms = pe0.elapsed_time(pe1)
-    agg = {}
+    pk, pk_kind = peaks()
+    hbm_bps, tc_fps = pk["hbm_gbs"] * 1e9, pk["bf16_tflops_sustained"] * 1e12
+
+    def nz(x):
+        return 1 if (x is not None and getattr(x, "value", x)) else 0
+
+    def work_of(name, a):
+        """(family, shape key, algorithmic bytes, flops) of one C-ABI call -- DESIGN.md section 4."""
+        if name == "mvk_kpconv_weighted":
+            nq, is64, h, cin, ld = a[1], a[5], a[6], a[8], a[14]
+            return "stage_a_fwd", f"[cin={cin}]", nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld), 0.0
+        if name == "mvk_kpconv_weighted_bwd":
+            nq, is64, h, cin, ld = a[1], a[5], a[6], a[7], a[14]
+            return "stage_a_bwd", f"[cin={cin}]", nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld), 0.0
+        if name == "mvk_gemm_bf16x3":
+            M, N, K, nv, terms = a[8], a[9], a[10], a[13], a[14]
+            ob = 4 if terms == 3 else 2  # bytes per operand element (hi + lo, or hi only)
+            return ("contraction", f"[M={M},N={N},K={K},amn={a[2]},bmn={a[6]},split={a[15]}]",
+                    ob * (M * K + K * N) + 4.0 * M * nv, 2.0 * M * N * K * terms)
+        if name == "mvk_col_stats":
+            return "bn_stream", f"[{a[1]}x{a[2]}]", 4.0 * a[1] * a[2], 0.0
+        if name == "mvk_scale_shift_act":
+            return "bn_stream", f"[{a[1]}x{a[2]}]", 4.0 * a[1] * a[2] * (2 + nz(a[6])), 0.0
+        if name == "mvk_act_bwd_reduce":
+            return "bn_stream", f"[{a[3]}x{a[4]}]", 4.0 * a[3] * a[4] * (2 + nz(a[8])), 0.0
+        if name == "mvk_act_bwd_apply":
+            n = a[3] * a[4]
+            return "bn_stream", f"[{a[3]}x{a[4]}]", 4.0 * n * (3 + nz(a[8]) + nz(a[20])), 0.0
+        if name == "mvk_split_bf16":
+            return "bn_stream", f"[{a[1]}x{a[2]}]", 8.0 * a[1] * a[2], 0.0
+        if name in ("mvk_neighbors_query_capped",):
+            nq, ns, width, is64 = a[1], a[3], a[10], a[13]
+            return "neighbors", "", nq * 12.0 + ns * 12.0 + nq * width * (8 if is64 else 4), 0.0
+        if name in ("mvk_neighbors_count", "mvk_neighbors_fill", "mvk_neighbors_fill_i64"):
+            return "neighbors", "", a[1] * 12.0 + a[3] * 12.0, 0.0
+        if name in ("mvk_pool", "mvk_pool_bwd"):
+            return "pools", "", 0.0, 0.0
+        return name.replace("mvk_", ""), "", 0.0, 0.0
+
+    agg, fam = {}, {}
     for name, a, s, e in records:
         d = s.elapsed_time(e)
-        key = name
-        work = 0.0
-        if name == "mvk_kpconv_weighted":
-            nq, is64, h, cin, K, ld = a[1], a[5], a[6], a[8], a[10], a[14]
-            key += f"[cin={cin}]"
-            # B_gi = H (idx + 12 + 4 Cin) + 12 read, + 4*15*Cin staged write (hi+lo bf16 = 4 B/elem)
-            work = nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld)
-        elif name == "mvk_kpconv_weighted_bwd":
-            nq, is64, h, cin, K, ld = a[1], a[5], a[6], a[7], a[9], a[14]
-            key += f"[cin={cin}]"
-            work = nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld)
-        elif name == "mvk_gemm_bf16x3":
-            M, N, K, terms = a[8], a[9], a[10], a[14]
-            key += f"[{'x'.join(map(str, (N, K)))}]"
-            work = 2.0 * M * N * K * terms
-        if name in ("mvk_col_stats", "mvk_scale_shift_act"):
-            key += f"[{a[1]}x{a[2]}]"
-        elif name in ("mvk_act_bwd_reduce", "mvk_act_bwd_apply"):
-            key += f"[{a[3]}x{a[4]}]"
-        elif name == "mvk_split_bf16":
-            key += f"[{a[1]}x{a[2]}]"
-        elif name == "mvk_gemm_bf16x3":
-            key = f"mvk_gemm_bf16x3[M={a[8]},N={a[9]},K={a[10]},amn={a[2]},bmn={a[6]},split={a[15]}]"
-        r = agg.setdefault(key, [0.0, 0, 0.0, name])
+        family, shape, nbytes, flops = work_of(name, a)
+        r = agg.setdefault(name + shape, [0.0, 0, name])
         r[0] += d
         r[1] += 1
-        r[2] += work
+        f = fam.setdefault(family, {"ms": 0.0, "calls": 0, "bytes": 0.0, "flops": 0.0, "ideal_ms": 0.0})
+        f["ms"] += d
+        f["calls"] += 1
+        f["bytes"] += nbytes
+        f["flops"] += flops
+        f["ideal_ms"] += 1e3 * max(nbytes / hbm_bps, flops / tc_fps)
     by_entry = {}
-    for key, (d, c, w, name) in agg.items():
-        r = by_entry.setdefault(name, [0.0, 0, 0.0])
+    for key, (d, c, name) in agg.items():
+        r = by_entry.setdefault(name, [0.0, 0])
         r[0] += d
         r[1] += c
-        r[2] += w
-    pk, pk_kind = peaks()
-    top = max(((n, v) for n, v in by_entry.items() if v[2] > 0), key=lambda kv: kv[1][0], default=None)
-    roofline = None
-    if top is not None:
-        name, (d, c, w) = top
-        if name == "mvk_gemm_bf16x3":
-            ach = w / (d * 1e-3) / 1e12
-            roofline = {"kernel": "gemm_tc_kernel (" + name + ")", "bound": "tensor", "achieved": round(ach, 2),
-                        "peak": pk["bf16_tflops_sustained"], "peak_kind": pk_kind + " sustained bf16", "unit": "TFLOP/s",
-                        "frac": round(ach / pk["bf16_tflops_sustained"], 4), "traffic": None}
+
+    def roof(family, f):
+        t = f["ms"] * 1e-3
+        hbm_bound = f["bytes"] / hbm_bps >= f["flops"] / tc_fps
+        if hbm_bound:
+            ach, peak, unit, kind = f["bytes"] / t / 1e9, pk["hbm_gbs"], "GB/s", pk_kind
         else:
-            ach = w / (d * 1e-3) / 1e9
-            kern = "kp_weighted_fwd" if name == "mvk_kpconv_weighted" else "kp_weighted_bwd"
-            roofline = {"kernel": kern + " (" + name + ")", "bound": "hbm", "achieved": round(ach, 1),
-                        "peak": pk["hbm_gbs"], "peak_kind": pk_kind, "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4),
-                        "traffic": None}
-        roofline["launches"] = c
-        roofline["avg_launch_us"] = round(1e3 * d / c, 2)
-        roofline["share_of_step"] = round(d / prof_ms, 4)
+            ach, peak, unit, kind = f["flops"] / t / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s", pk_kind + " sustained bf16"
+        return {"kernel": family, "bound": "hbm" if hbm_bound else "tensor", "achieved": round(ach, 1), "peak": peak,
+                "peak_kind": kind, "unit": unit, "frac": round(ach / peak, 4), "traffic": None, "launches": f["calls"],
+                "avg_launch_us": round(1e3 * f["ms"] / f["calls"], 2), "share_of_step": round(f["ms"] / prof_ms, 4),
+                "frac_of_mixed_roofline": round(f["ideal_ms"] / f["ms"], 4)}
+
+    KERNEL_OF = {"stage_a_fwd": "kp_fwd_fast / kp_fwd_tiny (mvk_kpconv_weighted)", "stage_a_bwd": "kp_bwd_fast (mvk_kpconv_weighted_bwd)",
+                 "contraction": "gemm_tc_kernel (mvk_gemm_bf16x3)", "bn_stream": "col_stats / scale_shift_act / act_bwd_* / split_bf16"}
+    rooflines = {k: roof(KERNEL_OF.get(k, k), f) for k, f in fam.items() if f["bytes"] > 0 or f["flops"] > 0}
+    top = max(rooflines.items(), key=lambda kv: fam[kv[0]]["ms"], default=(None, None))
+    roofline = top[1]
     breakdown = {n: {"ms_per_step": round(v[0] / args.steps, 3), "calls_per_step": v[1] // args.steps}
                  for n, v in sorted(by_entry.items(), key=lambda kv: -kv[1][0])}
     nb_ms = sum(v[0] for n, v in by_entry.items() if n.startswith("mvk_neighbors"))
@@ -284,7 +304,7 @@ def run_b200(args):
             "e2e": {"value": round(total_pts * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": 4 + 4 * 15},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "neighbor_queries_per_s": round(nb_qps, 1) if nb_qps else None,
             "neighbor_queries_per_step": int(queries_per_step[0]),
             "breakdown_ms": breakdown, "loss": loss_v,

@@ -139,7 +139,7 @@ class _LinearBNAct(torch.autograd.Function):
                 check(L.mvk_split_bf16(ptr(w), cout, cin, cin, ptr(w_hi), ptr(w_lo), cout, ldx, st))
                 if rows > 0:
                     check(L.mvk_gemm_bf16x3(ptr(x_hi), ptr(x_lo), 0, ldx, ptr(w_hi), ptr(w_lo), 0, ldx, rows, cout, cin,
-                                            ptr(y), cout, cout, terms, 1, st))
+                                            ptr(y), cout, cout, terms, 0, st))
                 ops = (x_hi, x_lo, w_hi, w_lo)
             scale, shift, mean, invstd = _norm_forward(L, y, rows, cout, use_bn, training, gamma, beta, rm, rv,
                                                        momentum, eps, st)
@@ -198,7 +198,7 @@ class _LinearBNAct(torch.autograd.Function):
                     if rows > 0:
                         # dx = dy W : A = dy [rows, cout] K-major, B = W stored [K = cout, N = cin] (N contiguous)
                         check(L.mvk_gemm_bf16x3(ptr(dy_hi), ptr(dy_lo), 0, ldh, ptr(w_hi), ptr(w_lo), 1, ldx, rows, cin,
-                                                cout, ptr(dx), cin, cin, terms, 1, st))
+                                                cout, ptr(dx), cin, cin, terms, 0, st))
                 if need_w:
                     dw = torch.zeros((cout, cin), dtype=torch.float32, device=dev)
                     if rows > 0:

@@ -384,6 +384,19 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
     p.b_mn = b_mn_major ? 1 : 0;
     p.bn = choose_bn(n_valid, p.b_mn != 0);
     p.kb_total = (K + BK - 1) / BK;
+    bool auto_split = false;
+    if (split_k == 0) {
+        // auto: few output tiles but a long reduction (the deep, small layers) -> spread K over the SMs;
+        // the library zeroes D itself in that case
+        const int tiles = ((M + BM - 1) / BM) * ((n_valid + p.bn - 1) / p.bn);
+        split_k = 1;
+        if (tiles * 2 <= num_sms() && p.kb_total >= 8) {
+            split_k = num_sms() / tiles;
+            if (split_k > p.kb_total / 4) split_k = p.kb_total / 4;
+            if (split_k < 1) split_k = 1;
+        }
+        auto_split = split_k > 1;
+    }
     if (split_k < 1) split_k = 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
     p.kb_per_split = (p.kb_total + split_k - 1) / split_k;
@@ -423,6 +436,8 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
     } else {
         md = ma_hi;  // unused
     }
+    if (auto_split && p.splits > 1)
+        MVK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)n_valid * 4, (size_t)M, (cudaStream_t)stream));
     const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + STAGING_BYTES;
     MVK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();

@@ -333,6 +333,34 @@ pool_fwd(const float* __restrict__ x, int ns, int c, const void* __restrict__ in
     }
 }
 
+// float4 flavour (c % 4 == 0): one 128-bit load per lane and neighbour, indices read once per row.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+pool_fwd_vec4(const float* __restrict__ x, int ns, int c, const void* __restrict__ inds, int nq, int h,
+              int mode, float* __restrict__ out, int* __restrict__ arg) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nq; i += gridDim.x * wpb) {
+        for (int ch = lane * 4; ch < c; ch += 128) {
+            float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
+            int4 bj = make_int4(ns, ns, ns, ns);
+            const int hh = mode == 1 ? 1 : h;
+            for (int t = 0; t < hh; t++) {
+                const int j = load_idx<IdxT>(inds, (size_t)i * h + t);
+                const bool real = j >= 0 && j < ns;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (real) v = __ldg((const float4*)(x + (size_t)j * c + ch));
+                const int jj = real ? j : ns;
+                if (t == 0 || v.x > best.x) { best.x = v.x; bj.x = jj; }
+                if (t == 0 || v.y > best.y) { best.y = v.y; bj.y = jj; }
+                if (t == 0 || v.z > best.z) { best.z = v.z; bj.z = jj; }
+                if (t == 0 || v.w > best.w) { best.w = v.w; bj.w = jj; }
+            }
+            *(float4*)(out + (size_t)i * c + ch) = best;
+            if (arg && mode == 0) *(int4*)(arg + (size_t)i * c + ch) = bj;
+        }
+    }
+}
+
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pool_bwd(const float* __restrict__ go, int nq, int c, const int* __restrict__ arg,
@@ -550,10 +578,11 @@ kp_fwd_tiny(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ o
         }
     }
     const size_t row = (size_t)i * a.ld;
-    if (out_hi && a.ld == KF * 4) {
-        // the whole 64-column bf16 row (zero padding included) as 8 + 8 128-bit stores
+    if (out_hi && (a.ld % 8) == 0 && a.ld <= KF * 4) {
+        // the whole bf16 row (zero padding included) as ld/8 + ld/8 128-bit stores
 #pragma unroll
         for (int v8 = 0; v8 < 8; v8++) {
+            if (v8 * 8 >= a.ld) break;
             unsigned int ph[4], pl[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -932,7 +961,12 @@ int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, in
     int blocks = (nq + 7) / 8;
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;
-    if (idx_is_i64)
+    if (c % 4 == 0 && (((size_t)x | (size_t)out | (size_t)arg_out) & 15) == 0) {
+        if (idx_is_i64)
+            pool_fwd_vec4<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+        else
+            pool_fwd_vec4<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+    } else if (idx_is_i64)
         pool_fwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
     else
         pool_fwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);

@@ -140,7 +140,7 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
     const unsigned int mask = g.cap - 1;
     const int nq_valid = min(nq, g.q_starts[nb]);
     if (*g.err != 0) {  // a support fell outside the indexable cell range: report, do nothing
-        if (!WRITE && blockIdx.x == 0 && threadIdx.x == 0) *max_count = -1;
+        if (max_count && blockIdx.x == 0 && threadIdx.x == 0) *max_count = -1;
         return;
     }
 
@@ -201,6 +201,10 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
                 if (nfound > 0) atomicMax(max_count, nfound);
             }
         } else {
+            if (max_count && lane == 0) {  // single-pass protocol: the caller checks max_count <= list_cap
+                if (counts) counts[i] = nfound;
+                if (nfound > 0) atomicMax(max_count, nfound);
+            }
             __syncwarp();
             int n = min(nfound, list_cap);
             OutT* row = out + (size_t)i * width;
@@ -269,6 +273,38 @@ int fill(const float* q, int nq, const float* s, int ns, int nb, float radius, v
     return MVK_OK;
 }
 
+template <typename OutT>
+int query_capped(const float* q, int nq, const float* s, int ns, const int* ql, const int* sl, int nb, float radius,
+                 void* ws, size_t ws_bytes, int width, int list_cap, OutT* out, int* counts, int* max_count,
+                 cudaStream_t st) {
+    if (nq < 0 || ns < 0 || nb < 1 || nb > 1023 || !(radius > 0.f) || width < 1 || list_cap < width || !out ||
+        !max_count)
+        return MVK_ERR_INVALID_ARG;
+    if (ws_bytes < mvk_neighbors_workspace_bytes(nq, ns, nb) || !ws) return MVK_ERR_WORKSPACE;
+    Arena a(ws, ws_bytes);
+    Grid g = carve(a, nq, ns, nb);
+    int rc = build(s, ns, ql, sl, nb, radius, g, st);
+    if (rc) return rc;
+    MVK_CUDA(cudaMemsetAsync(max_count, 0, sizeof(int), st));
+    if (nq == 0) return MVK_OK;
+    list_cap = (list_cap + 31) / 32 * 32;
+    size_t per_warp = (size_t)list_cap * 8;
+    if (per_warp > 200 * 1024) return MVK_ERR_RANGE;
+    int wpb = (int)((64 * 1024) / per_warp);
+    wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
+    size_t smem = per_warp * wpb;
+    auto kern = k_query<true, OutT>;
+    MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = (nq + wpb - 1) / wpb;
+    int max_blocks = num_sms() * 32;
+    if (blocks > max_blocks) blocks = max_blocks;
+    float r2 = radius * radius;
+    double inv_cell = 1.0 / ((double)radius * 1.00001);
+    kern<<<blocks, wpb * 32, smem, st>>>(q, nq, nb, r2, inv_cell, g, counts, max_count, list_cap, width, out, ns);
+    MVK_LAUNCHED("k_query<capped>");
+    return MVK_OK;
+}
+
 }  // namespace
 }  // namespace mvk
 
@@ -324,6 +360,17 @@ int mvk_neighbors_fill_i64(const float* queries, int nq, const float* supports, 
     (void)s_lengths;
     return fill<long long>(queries, nq, supports, ns, nb, radius, ws, ws_bytes, max_count, width,
                            out, (cudaStream_t)stream);
+}
+
+int mvk_neighbors_query_capped(const float* queries, int nq, const float* supports, int ns, const int* q_lengths,
+                               const int* s_lengths, int nb, float radius, void* ws, size_t ws_bytes, int width,
+                               int list_cap, void* out, int out_is_i64, int* counts, int* max_count,
+                               mvk_stream_t stream) {
+    if (out_is_i64)
+        return query_capped<long long>(queries, nq, supports, ns, q_lengths, s_lengths, nb, radius, ws, ws_bytes, width,
+                                       list_cap, (long long*)out, counts, max_count, (cudaStream_t)stream);
+    return query_capped<int>(queries, nq, supports, ns, q_lengths, s_lengths, nb, radius, ws, ws_bytes, width, list_cap,
+                             (int*)out, counts, max_count, (cudaStream_t)stream);
 }
 
 int mvk_batch_neighbors_host(const float* qh, int nq, const float* sh, int ns, const int* qlh,

@@ -95,6 +95,26 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
         ws = _workspace(wsb, dev)
         counts = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
         hmax = torch.zeros(1, dtype=torch.int32, device=dev)
+        if max_neighbors is not None and nq > 0:
+            # the row width is capped by the caller: one query pass (no separate count pass)
+            width = max(1, int(max_neighbors))
+            cap = max(128, (width + 31) // 32 * 32)
+            out = torch.empty((nq, width), dtype=out_dtype, device=dev)
+            check(L.mvk_neighbors_query_capped(ptr(q), nq, ptr(s), ns, ptr(qb), ptr(sb), nb, float(radius), ptr(ws),
+                                               ws.numel(), width, cap, ptr(out), 1 if out_dtype == torch.int64 else 0,
+                                               ptr(counts), ptr(hmax), stream_ptr()))
+            max_count = int(hmax.item())  # the one host sync
+            if max_count < 0:
+                check(-4)
+            if max_count < 1:
+                raise RuntimeError("Error")  # cpp_neighbors/wrapper.cpp:201-205
+            if max_count <= cap:
+                if max_count < width:
+                    out = out[:, :max_count].contiguous()  # reference width = min(max_count, limit)
+                if as_np:
+                    out, counts = out.cpu().numpy(), counts.cpu().numpy()
+                return (out, counts[:nq]) if return_counts else out
+            # more hits than the shared-memory lists hold somewhere: redo with the two-phase protocol
         check(L.mvk_neighbors_count(ptr(q), nq, ptr(s), ns, ptr(qb), ptr(sb), nb, float(radius),
                                     ptr(ws), ws.numel(), ptr(counts), ptr(hmax), stream_ptr()))
         max_count = int(hmax.item())  # the one host sync: the row width is data dependent

@@ -84,8 +84,8 @@ class _KPConvFunction(torch.autograd.Function):
                 saved = (A,)
             else:
                 terms = 3 if contraction == "bf16x3" else 1
-                ld = _round_up(kd, 64)
-                npad = _round_up(cout, 64)
+                ld = _round_up(kd, 8)      # 16-byte row pitch is all TMA needs: partial tiles are zero-filled
+                npad = _round_up(cout, 8)
                 a_hi = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
                 a_lo = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
                 check(L.mvk_kpconv_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin,
@@ -96,7 +96,7 @@ class _KPConvFunction(torch.autograd.Function):
                 check(L.mvk_split_bf16(ptr(w), kd, cout, cout, ptr(w_hi), ptr(w_lo), ld, npad, st))
                 if nq > 0:
                     check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, ld, ptr(w_hi), ptr(w_lo), 1, npad,
-                                            nq, npad, ld, ptr(out), cout, cout, terms, 1, st))
+                                            nq, npad, ld, ptr(out), cout, cout, terms, 0, st))
                 saved = (a_hi, a_lo, w_hi, w_lo)
         ctx.save_for_backward(q, s, inds, kp, w, *saved)
         ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64)
@@ -149,7 +149,7 @@ class _KPConvFunction(torch.autograd.Function):
                     if nq > 0:
                         # dA = dOut W^T : A = dOut [nq, npad] K-major, B = W [ld, npad] K-major
                         check(L.mvk_gemm_bf16x3(ptr(go_hi), ptr(go_lo), 0, npad, ptr(w_hi), ptr(w_lo), 0, npad,
-                                                nq, ld, npad, ptr(dA), ld, ld, terms, 1, st))
+                                                nq, ld, npad, ptr(dA), ld, ld, terms, 0, st))
             if need_x:
                 gx = torch.zeros((ns, cin), dtype=torch.float32, device=dev)
                 check(L.mvk_kpconv_weighted_bwd(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, cin, ptr(kp), K,

@@ -72,6 +72,17 @@ int mvk_neighbors_fill_i64(const float* queries, int nq, const float* supports, 
                            const int* q_lengths, const int* s_lengths, int nb, float radius,
                            void* ws, size_t ws_bytes, int max_count, int width, long long* out,
                            mvk_stream_t stream);
+/* Single-pass variant for callers that crop the rows anyway (the pyramid builder: big_neighborhood_filter,
+ * datasets/common.py:411-421): builds the grid and writes out[nq, width] = the `width` nearest
+ * neighbours per row in one query pass, collecting up to list_cap hits per query in shared memory.
+ * *max_count (device int) receives the true maximum hit count: if it exceeds list_cap the rows of
+ * such queries may be wrong and the caller must fall back to the two-phase protocol; if it is
+ * smaller than width the caller crops the columns (reference width = min(max_count, limit)).
+ * counts may be NULL. */
+int mvk_neighbors_query_capped(const float* queries, int nq, const float* supports, int ns, const int* q_lengths,
+                               const int* s_lengths, int nb, float radius, void* ws, size_t ws_bytes, int width,
+                               int list_cap, void* out, int out_is_i64, int* counts, int* max_count,
+                               mvk_stream_t stream);
 /* Host-buffer convenience entry point == the reference call: all pointers are HOST pointers,
  * *out_host is malloc'ed [nq, *width] int32 (free with mvk_free_host).  Copies H2D, runs both
  * phases on the default stream, copies D2H.  Returns MVK_ERR_EMPTY when nq * max_count == 0
@@ -152,7 +163,8 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
  * M, N, K are the true extents: tiles that reach past them are zero-filled by TMA (out-of-bounds
  * fill), so no operand padding is needed; lda/ldb must be multiples of 8 elements (16-byte row
  * pitch) and the base pointers 16-byte aligned.  n_valid <= N columns of D are written.
- * split_k > 1 partitions K over CTAs and accumulates into D with fp32 atomics (D must be zeroed). */
+ * split_k > 1 partitions K over CTAs and accumulates into D with fp32 reductions (D must be zeroed
+ * by the caller); split_k = 0 lets the library decide (it zeroes D itself when it splits). */
 int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
                     const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
                     int n_valid, int terms, int split_k, mvk_stream_t stream);
