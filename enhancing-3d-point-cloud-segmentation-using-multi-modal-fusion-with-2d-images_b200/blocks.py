@@ -49,12 +49,14 @@ def _norm_forward(L, y, rows, cols, use_bn, training, gamma, beta, rm, rv, momen
     shift = torch.empty_like(scale)
     mean = torch.empty_like(scale)
     invstd = torch.empty_like(scale)
-    stats = None
-    if training:
-        stats = torch.zeros(2 * cols, dtype=torch.float64, device=dev)
-        check(L.mvk_col_stats(ptr(y), rows, cols, y.stride(0), ptr(stats), st))
-    check(L.mvk_bn_finalize(ptr(stats), rows, cols, ptr(gamma.detach()), ptr(beta.detach()), eps, momentum,
-                            1 if training else 0, ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), st))
+    if training and rows > 0:
+        # column sums and, in the CTA that retires last, scale / shift / running statistics: one launch
+        stats = torch.zeros(2 * cols + 1, dtype=torch.float64, device=dev)
+        check(L.mvk_bn_batch_stats(ptr(y), rows, cols, y.stride(0), ptr(stats), ptr(gamma.detach()), ptr(beta.detach()),
+                                   eps, momentum, ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), st))
+    else:
+        check(L.mvk_bn_finalize(None, rows, cols, ptr(gamma.detach()), ptr(beta.detach()), eps, momentum, 0, ptr(rm),
+                                ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), st))
     return scale, shift, mean, invstd
 
 

@@ -17,6 +17,7 @@
 // so the forward product (A K-major, W MN-major), dX-side product (both K-major) and the dW product
 // (both MN-major, split over K with atomics) all run through this one kernel without transposes.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -27,14 +28,14 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int MAX_STAGES = 8;
 constexpr int A_TILE_BYTES = 16384;            // 128 rows x 128 B (one of hi / lo)
-constexpr int NUM_THREADS = 192;
-constexpr int STAGING_BYTES = 4 * 2 * 4096;    // 4 epilogue warps x 2 buffers x [32 rows x 128 B]
+constexpr int MAX_THREADS = 320;               // 2 + up to 8 epilogue warps
+constexpr int STAGING_PER_WARP = 2 * 4096;     // 2 buffers x [32 rows x 128 B] per epilogue warp
 constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
 struct GemmParams {
     float* D;
     int M, N, ldd, bn, kb_total, kb_per_split, splits, terms, a_mn, b_mn, atomic_out, stages, tma_store;
-    int m_tiles, n_tiles, num_tiles, tmem_cols, stage_bytes;
+    int m_tiles, n_tiles, num_tiles, tmem_cols, stage_bytes, ew, d_swizzle;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -109,11 +110,50 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 16 TMEM lanes x 64 columns in the accumulator-fragment layout: lane t holds, for column block i,
+// v[4i], v[4i+1] = (row t/4, cols 8i + 2(t%4) + {0,1}) and v[4i+2], v[4i+3] = (row t/4 + 8, same cols)
+// -- a quad of lanes covers one full 32-byte sector of a row, so plain vector stores are sector-exact.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+
+// Stores one 16-row x 64-column fragment (see tmem_ld_16x256b_x8); static register indices only.
+__device__ __forceinline__ void frag_store(const uint32_t (&v)[32], const GemmParams& p, int r_lo, int col0, int lane) {
+#pragma unroll
+    for (int rr = 0; rr < 2; rr++) {
+        const int r = r_lo + rr * 8;
+        if (r < p.M) {
+            float* drow = p.D + (size_t)r * p.ldd + col0 + 2 * (lane & 3);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (col0 + 8 * i + 2 * (lane & 3) + 1 < p.N) {
+                    const float a = __uint_as_float(v[4 * i + 2 * rr]);
+                    const float b = __uint_as_float(v[4 * i + 2 * rr + 1]);
+                    if (p.atomic_out) red_add_v2(drow + 8 * i, a, b);
+                    else *(float2*)(drow + 8 * i) = make_float2(a, b);
+                }
+            }
+        }
+    }
+}
+
 // Persistent, warp-specialised: every CTA (one per SM) walks the tile list t = blockIdx.x,
 // blockIdx.x + gridDim.x, ...; tile -> (split, m, n) with n fastest so that the CTAs working on
 // one row block share its A tile through L2.  The smem ring and the two TMEM accumulator buffers
 // run across tile boundaries, so the loads / MMAs of tile i+1 overlap the epilogue of tile i.
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(MAX_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                const __grid_constant__ CUtensorMap tm_d, GemmParams p) {
@@ -142,7 +182,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(bar_tfull + 8 * b, 1);
-            mbar_init(bar_tempty + 8 * b, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * b, (uint32_t)p.ew);  // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -245,8 +285,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         }
     } else {
         // ===================== epilogue =====================
-        const int quarter = warp & 3;  // TMEM lanes [32q, 32q+32) are only visible to warps with id%4 == q
-        const uint32_t my_stage = staging + (uint32_t)(warp - 2) * 8192u;
+        // TMEM lanes [32q, 32q+32) are only visible to warps with id%4 == q.  With 8 epilogue warps
+        // (output-bound shapes) two warps share a lane quarter and take alternate 32-column chunks.
+        const int quarter = warp & 3;
+        const int nhalf = p.ew >> 2, half = (warp - 2) >> 2;
+        const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (uint32_t)STAGING_PER_WARP;
         int it = 0;
         int sbuf = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
@@ -258,36 +301,61 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int row = m0 + quarter * 32 + lane;
             const bool rows_live = (m0 + quarter * 32) < p.M;
-            for (int c0 = 0; c0 < p.bn; c0 += 32) {
+            if (p.tma_store == 2) {
+                // fragment-layout epilogue: TMEM -> registers -> sector-exact 8-byte global stores
+                // (or vector reductions for split-K); no shared-memory staging, no proxy fences.
+                if (rows_live) {
+                    const int r_lo = m0 + quarter * 32 + (lane >> 2);
+                    for (int c0 = 0; c0 < p.bn; c0 += 64) {
+                        if (n0 + c0 >= p.N) break;
+                        uint32_t va[32], vb[32];
+                        const uint32_t tcol = (uint32_t)(buf * p.bn + c0);
+                        tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol, va);
+                        tmem_ld_16x256b_x8(tmem_base + ((uint32_t)(quarter * 32 + 16) << 16) + tcol, vb);
+                        tmem_wait_ld();
+                        frag_store(va, p, r_lo, n0 + c0, lane);
+                        frag_store(vb, p, r_lo + 16, n0 + c0, lane);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+                continue;
+            }
+            for (int c0 = half * 32; c0 < p.bn; c0 += 32 * nhalf) {
                 if (n0 + c0 >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(buf * p.bn + c0), v);
-                if (!rows_live) continue;
+                if (!rows_live && !p.tma_store) continue;
                 if (p.tma_store) {
-                    // registers -> 128B-swizzled staging tile [32 rows x 32 cols] -> TMA store (clips at M, N)
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                    const uint32_t dst = my_stage + (uint32_t)sbuf * 4096u + (uint32_t)lane * 128u;
+                    // registers -> 128B-swizzled staging tile [128 rows x 32 cols] shared by the four
+                    // epilogue warps -> ONE TMA store per chunk (clips at M, N)
+                    const uint32_t tile = staging + (uint32_t)sbuf * 16384u;
+                    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const uint32_t dst = tile + (uint32_t)(quarter * 32 + lane) * 128u;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const uint32_t addr = dst + (uint32_t)((j ^ (lane & 7)) << 4);
+                        const uint32_t addr = dst + (uint32_t)((p.d_swizzle ? (j ^ (lane & 7)) : j) << 4);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * j]),
                                      "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3]) : "memory");
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tm_d, my_stage + (uint32_t)sbuf * 4096u, n0 + c0, m0 + quarter * 32, p.atomic_out);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (warp == 2 && lane == 0) {
+                        tma_store_2d(&tm_d, tile, n0 + c0, m0, p.atomic_out);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     sbuf ^= 1;
                 } else if (row < p.M) {
                     float* dst = p.D + (size_t)row * p.ldd + n0 + c0;
                     const int ncols = min(32, p.N - (n0 + c0));
-                    if (p.atomic_out) {
-                        for (int j = 0; j < ncols; j++) atomicAdd(dst + j, __uint_as_float(v[j]));
-                    } else {
-                        for (int j = 0; j < ncols; j++) dst[j] = __uint_as_float(v[j]);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {  // static indices keep v[] in registers
+                        if (j < ncols) {
+                            if (p.atomic_out) atomicAdd(dst + j, __uint_as_float(v[j]));
+                            else dst[j] = __uint_as_float(v[j]);
+                        }
                     }
                 }
             }
@@ -296,7 +364,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -324,7 +392,7 @@ EncodeTiledFn encode_fn() {
 
 // 2D tensor map: inner (contiguous) extent d0, outer extent d1, row pitch ld elements of esize bytes.
 int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t box0, uint32_t box1,
-             int esize = 2) {
+             int esize = 2, bool swizzle = true) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled entry point unavailable");
@@ -335,7 +403,8 @@ int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base,
-                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -345,16 +414,16 @@ int make_map(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_
 }
 
 // Widest N tile whose padding waste stays small: wide tiles re-read the A operand least.
-int choose_bn(int N, bool b_mn) {
+int choose_bn(int N, bool b_mn, int max_bn) {
     const int cands[4] = {256, 128, 64, 32};
     int min_pad = 1 << 30;
     for (int i = 0; i < 4; i++) {
-        if (b_mn && cands[i] < 64) continue;
+        if ((b_mn && cands[i] < 64) || cands[i] > max_bn) continue;
         int pad = (N + cands[i] - 1) / cands[i] * cands[i];
         if (pad < min_pad) min_pad = pad;
     }
     for (int i = 0; i < 4; i++) {
-        if (b_mn && cands[i] < 64) continue;
+        if ((b_mn && cands[i] < 64) || cands[i] > max_bn) continue;
         int pad = (N + cands[i] - 1) / cands[i] * cands[i];
         if ((long long)pad * 100 <= (long long)min_pad * 115) return cands[i];
     }
@@ -382,7 +451,18 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
     p.ldd = ldd;
     p.a_mn = a_mn_major ? 1 : 0;
     p.b_mn = b_mn_major ? 1 : 0;
-    p.bn = choose_bn(n_valid, p.b_mn != 0);
+    p.kb_total = (K + BK - 1) / BK;
+    // output-bound shapes (short reductions): 8 epilogue warps, tiles at most 128 wide
+    p.ew = 4;
+    {
+        static const char* e_ew = getenv("MVK_GEMM_EW");
+        (void)e_ew;
+    }
+    p.bn = choose_bn(n_valid, p.b_mn != 0, p.ew == 8 ? 128 : 256);
+    {
+        static const char* e_bn = getenv("MVK_GEMM_BN");
+        if (e_bn && atoi(e_bn) >= 32 && (!p.b_mn || atoi(e_bn) >= 64)) p.bn = atoi(e_bn);
+    }
     p.kb_total = (K + BK - 1) / BK;
     bool auto_split = false;
     if (split_k == 0) {
@@ -409,9 +489,20 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
     p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
-    p.stages = (SMEM_LIMIT - 2048 - STAGING_BYTES) / p.stage_bytes;  // 1 KB alignment slack + static smem
+    const int staging_bytes = p.ew * STAGING_PER_WARP;
+    p.stages = (SMEM_LIMIT - 2048 - staging_bytes) / p.stage_bytes;  // 1 KB alignment slack + static smem
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tma_store = ((ldd % 4) == 0 && (((size_t)D) & 15) == 0) ? 1 : 0;
+    // output row pitch not a multiple of 16 bytes: fragment-layout epilogue (8-byte sector-exact stores)
+    if (!p.tma_store && (n_valid % 2) == 0 && (ldd % 2) == 0 && (((size_t)D) & 7) == 0) p.tma_store = 2;
+    {   // development overrides (scripts/gemm_bench.py)
+        static const char* e_store = getenv("MVK_GEMM_TMA_STORE");
+        if (e_store && e_store[0] == '2' && (n_valid % 2) == 0 && (ldd % 2) == 0) p.tma_store = 2;
+        if (e_store && e_store[0] == '1' && (ldd % 4) == 0) p.tma_store = 1;
+        static const char* e_stages = getenv("MVK_GEMM_STAGES");
+        if (e_store && e_store[0] == '0') p.tma_store = 0;
+        if (e_stages && atoi(e_stages) >= 1 && atoi(e_stages) < p.stages) p.stages = atoi(e_stages);
+    }
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, md;
     int rc;
@@ -431,17 +522,19 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
         if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, 64, 64))) return rc;
         if ((rc = make_map(&mb_lo, bl, N, K, ldb, 64, 64))) return rc;
     }
-    if (p.tma_store) {
-        if ((rc = make_map(&md, D, n_valid, M, ldd, 32, 32, 4))) return rc;
+    if (p.tma_store == 1) {
+        p.d_swizzle = 1;
+        if ((rc = make_map(&md, D, n_valid, M, ldd, 32, 128, 4, p.d_swizzle != 0))) return rc;
     } else {
         md = ma_hi;  // unused
+        p.d_swizzle = 0;
     }
     if (auto_split && p.splits > 1)
         MVK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)n_valid * 4, (size_t)M, (cudaStream_t)stream));
-    const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + STAGING_BYTES;
+    const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + staging_bytes;
     MVK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    gemm_tc_kernel<<<grid, NUM_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+    gemm_tc_kernel<<<grid, 64 + 32 * p.ew, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
     MVK_LAUNCHED("gemm_tc_kernel");
     return MVK_OK;
 }

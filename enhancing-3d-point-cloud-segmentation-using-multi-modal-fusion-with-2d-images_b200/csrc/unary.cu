@@ -98,11 +98,45 @@ __device__ __forceinline__ void reduce_columns(float (&part)[NV][VEC], float* re
     }
 }
 
+struct BnFin {
+    const float* gamma;
+    const float* beta;
+    float eps, momentum;
+    float* running_mean;
+    float* running_var;
+    float* scale;
+    float* shift;
+    float* mean_out;
+    float* invstd_out;
+    unsigned int* ticket;  // zero-initialised by the caller; NULL = no fused finalize
+};
+
+__device__ __forceinline__ void bn_finalize_column(const double s0, const double s1, int rows, int c, const BnFin& f) {
+    const double mu = s0 / rows;
+    double var = s1 / rows - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mu;
+    const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
+    if (f.running_mean) {
+        const double unbiased = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+    }
+    const float g = f.gamma ? f.gamma[c] : 1.f;
+    const float b = f.beta ? f.beta[c] : 0.f;
+    f.scale[c] = g * invstd;
+    f.shift[c] = b - mean * g * invstd;
+    if (f.mean_out) f.mean_out[c] = mean;
+    if (f.invstd_out) f.invstd_out[c] = invstd;
+}
+
 // stats[c] += sum_r y[r,c] ; stats[cols + c] += sum_r y[r,c]^2
 template <int VEC>
 __global__ void __launch_bounds__(TB)
-col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double* __restrict__ stats, int rows_per_cta) {
+col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double* __restrict__ stats, int rows_per_cta,
+                 BnFin fin) {
     __shared__ float red[2 * TB * VEC];
+    __shared__ unsigned int s_last;
     const Map2D m = make_map2d(cols, VEC);
     const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
     const bool active = ty < m.rpi;
@@ -138,6 +172,20 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
             }
         }
         reduce_columns<VEC, 2>(part, red, m, tx, ty, cok, c0, cols, stats);
+    }
+    if (fin.ticket) {
+        // the CTA that retires last turns the column sums into scale / shift / running statistics
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int c = threadIdx.x; c < cols; c += TB) {
+                const double s0 = __ldcg(stats + c), s1 = __ldcg(stats + cols + c);
+                bn_finalize_column(s0, s1, rows, c, fin);
+            }
+        }
     }
 }
 
@@ -278,7 +326,14 @@ act_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __rest
                      const float* __restrict__ residual, int ldr, const float* __restrict__ mean,
                      const float* __restrict__ invstd, float slope, const double* __restrict__ sums, int batch_stats,
                      float* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                     int ldh, float* __restrict__ dres, int lddres) {
+                     int ldh, float* __restrict__ dres, int lddres, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+    if (blockIdx.x == 0 && sums) {
+        for (int c = threadIdx.x; c < cols; c += TB) {
+            if (dbeta) dbeta[c] = (float)sums[c];
+            if (dgamma) dgamma[c] = (float)sums[cols + c];
+        }
+    }
     const int cv = cols / VEC;
     const size_t total = (size_t)rows * cv;
     const float inv_rows = 1.f / (float)rows;
@@ -324,9 +379,7 @@ inline int vec_for(int cols, int a, int b, int c, int d) {
 }
 inline int slab_rows(int rows, int cols, int vec, int* grid) {
     Map2D m = make_map2d(cols, vec);
-    int target = num_sms() * 8;
-    const int by_atomics = (96 * 1024) / (2 * cols);  // fp64 atomics per launch stay ~100k
-    if (target > by_atomics) target = by_atomics < 32 ? 32 : by_atomics;
+    int target = num_sms() * 2;  // same-address fp64 atomics serialise in L2: few, fat CTAs
     int rpc = (rows + target - 1) / target;
     rpc = (rpc + m.rpi - 1) / m.rpi * m.rpi;
     if (rpc < m.rpi * 4) rpc = m.rpi * 4;
@@ -352,9 +405,25 @@ int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk
     const int vec = vec_for(cols, ld, 4, 4, 4);
     int grid;
     const int rpc = slab_rows(rows, cols, vec, &grid);
-    if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc);
-    else col_stats_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc);
+    BnFin fin = {};
+    if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
+    else col_stats_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
     MVK_LAUNCHED("col_stats");
+    return MVK_OK;
+}
+
+int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       float* scale, float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream) {
+    if (!y || !stats || rows < 1 || cols < 1 || ld < cols || !scale || !shift) return MVK_ERR_INVALID_ARG;
+    const int vec = vec_for(cols, ld, 4, 4, 4);
+    int grid;
+    const int rpc = slab_rows(rows, cols, vec, &grid);
+    BnFin fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean_out, invstd_out,
+                 (unsigned int*)(stats + 2 * (size_t)cols)};
+    if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
+    else col_stats_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
+    MVK_LAUNCHED("col_stats+finalize");
     return MVK_OK;
 }
 
@@ -425,14 +494,15 @@ int mvk_act_bwd_apply(const float* dz, int lddz, const float* y, int rows, int c
         if (vec == 4)
             act_bwd_apply_kernel<4><<<grid, TB, 0, st>>>(dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
                                                          invstd, slope, sums, batch_stats, dy, lddy,
-                                                         (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres);
+                                                         (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres,
+                                                         dgamma, dbeta);
         else
             act_bwd_apply_kernel<1><<<grid, TB, 0, st>>>(dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
                                                          invstd, slope, sums, batch_stats, dy, lddy,
-                                                         (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres);
+                                                         (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres,
+                                                         dgamma, dbeta);
         MVK_LAUNCHED("act_bwd_apply");
-    }
-    if ((dgamma || dbeta) && sums) {
+    } else if ((dgamma || dbeta) && sums) {
         bn_param_grads_kernel<<<(cols + 255) / 256, 256, 0, st>>>(sums, cols, dgamma, dbeta);
         MVK_LAUNCHED("bn_param_grads");
     }
