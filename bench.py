@@ -136,6 +136,7 @@ def run_b200(args):
     opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3)
     feats_d, labels_d = feats_p.to(dev), labels_p.to(dev)
     queries_per_step = [0]
+    host_enqueue_ms = [0.0]
 
     def step(from_host):
         if from_host:
@@ -170,9 +171,11 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
+        t_host0 = time.perf_counter()
         for _ in range(steps):
             last = step(from_host)
         e1.record()
+        host_enqueue_ms[0] = 1e3 * (time.perf_counter() - t_host0) / steps  # host time to ENQUEUE a step
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -186,10 +189,11 @@ def run_b200(args):
         return ms, L.mvk_launch_count() - l0, clocks, float(last)
 
     ms, launches, clocks, loss_v = timed(False, args.steps, args.warmup, sample_clocks=True)
+    enqueue_ms = host_enqueue_ms[0]
     if args.quick:  # profiling runs (ncu): only the device-resident timed region
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": round(ms / args.steps, 3), "points": n_pts,
-                              "gpu_launches": int(launches)}), flush=True)
+                              "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(enqueue_ms, 3)}), flush=True)
         return
     ms_e2e, _, _, _ = timed(True, args.steps, max(1, args.warmup // 2))
 
@@ -307,7 +311,7 @@ def run_b200(args):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
             "neighbor_queries_per_s": round(nb_qps, 1) if nb_qps else None,
             "neighbor_queries_per_step": int(queries_per_step[0]),
-            "breakdown_ms": breakdown, "loss": loss_v,
+            "breakdown_ms": breakdown, "loss": loss_v, "host_enqueue_ms_per_step": round(enqueue_ms, 3),
         }
         if args.detail:
             det = sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.detail]

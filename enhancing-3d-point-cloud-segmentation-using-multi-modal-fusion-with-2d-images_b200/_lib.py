@@ -38,7 +38,7 @@ SIGNATURES = {
     "mvk_gemm_bf16x3": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
     "mvk_gemm_f32": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp, i32, i32, vp]),
     "mvk_col_stats": (i32, [vp, i32, i32, i32, vp, vp]),
-    "mvk_bn_batch_stats": (i32, [vp, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "mvk_bn_batch_stats": (i32, [vp, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "mvk_bn_finalize": (i32, [vp, i32, i32, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "mvk_scale_shift_act": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, f32, vp, i32, vp, vp, i32, vp]),
     "mvk_act_bwd_reduce": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, vp, vp]),
@@ -146,6 +146,36 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("mvkpconv_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     lib()
+
+
+class _ZeroPool:
+    """Small zero-initialised scratch buffers (batch-norm sums, retirement tickets) carved out of
+    one larger zeroed allocation: one fill per ~4 MB instead of one per buffer.  Slices are never
+    reused; the chunk is dropped when exhausted (the caching allocator recycles it once the slices die)."""
+    CHUNK = 4 << 20
+
+    def __init__(self):
+        self.buf, self.off, self.key = None, 0, None
+
+    def take(self, nbytes, device, dtype):
+        import torch
+        nbytes = (nbytes + 255) // 256 * 256
+        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        if nbytes > self.CHUNK // 4:
+            return torch.zeros(nbytes, dtype=torch.uint8, device=device).view(dtype)
+        if self.buf is None or self.key != key or self.off + nbytes > self.CHUNK:
+            self.buf, self.off, self.key = torch.zeros(self.CHUNK, dtype=torch.uint8, device=device), 0, key
+        out = self.buf[self.off:self.off + nbytes].view(dtype)
+        self.off += nbytes
+        return out
+
+
+_ZEROS = _ZeroPool()
+
+
+def zeros_f64(n, device):
+    """n zero-initialised doubles (pooled)."""
+    return _ZEROS.take(8 * n, device, __import__("torch").float64)[:n]
 
 
 def stream_ptr():

@@ -40,7 +40,7 @@ def _bn_args(bn_block):
     return (False, None, bn_block.bias, None, None, 0.0, 0.0, False, None)
 
 
-def _norm_forward(L, y, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st):
+def _norm_forward(L, y, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st, nbt=None):
     """-> scale, shift, mean, invstd (device [cols] vectors, None where unused)."""
     dev = y.device
     if not use_bn:
@@ -51,9 +51,10 @@ def _norm_forward(L, y, rows, cols, use_bn, training, gamma, beta, rm, rv, momen
     invstd = torch.empty_like(scale)
     if training and rows > 0:
         # column sums and, in the CTA that retires last, scale / shift / running statistics: one launch
-        stats = torch.zeros(2 * cols + 1, dtype=torch.float64, device=dev)
+        stats = _lib.zeros_f64(2 * cols + 1, dev)
         check(L.mvk_bn_batch_stats(ptr(y), rows, cols, y.stride(0), ptr(stats), ptr(gamma.detach()), ptr(beta.detach()),
-                                   eps, momentum, ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), st))
+                                   eps, momentum, ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+                                   ptr(nbt), st))
     else:
         check(L.mvk_bn_finalize(None, rows, cols, ptr(gamma.detach()), ptr(beta.detach()), eps, momentum, 0, ptr(rm),
                                 ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), st))
@@ -64,7 +65,7 @@ class _BNAct(torch.autograd.Function):
     """z = leaky(bn(y) [+ residual]); blocks.py:446-460 + the activation / residual that follows."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope):
+    def forward(ctx, y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, nbt=None):
         _lib.require_cuda()
         L = _lib.lib()
         if not y.is_cuda:
@@ -75,7 +76,7 @@ class _BNAct(torch.autograd.Function):
         st = stream_ptr()
         with torch.cuda.device(yf.device):
             scale, shift, mean, invstd = _norm_forward(L, yf, rows, cols, use_bn, training, gamma, beta, rm, rv,
-                                                       momentum, eps, st)
+                                                       momentum, eps, st, nbt)
             z = torch.empty_like(yf)
             check(L.mvk_scale_shift_act(ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res), cols, slope,
                                         ptr(z), cols, None, None, 0, st))
@@ -94,7 +95,7 @@ class _BNAct(torch.autograd.Function):
         need_y, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[3]
         batch_stats = 1 if (use_bn and training) else 0
         with torch.cuda.device(dev):
-            sums = torch.zeros(2 * cols, dtype=torch.float64, device=dev)
+            sums = _lib.zeros_f64(2 * cols, dev)
             if has_g or has_b or batch_stats:
                 check(L.mvk_act_bwd_reduce(ptr(g), cols, ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res),
                                            cols, ptr(mean), ptr(invstd), slope, ptr(sums), st))
@@ -105,14 +106,15 @@ class _BNAct(torch.autograd.Function):
             check(L.mvk_act_bwd_apply(ptr(g), cols, ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res), cols,
                                       ptr(mean), ptr(invstd), slope, ptr(sums), batch_stats, ptr(dy), cols, None, None,
                                       0, ptr(dres), cols, ptr(dgamma), ptr(dbeta), st))
-        return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None
+        return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None
 
 
 class _LinearBNAct(torch.autograd.Function):
     """z = leaky(bn(x W^T) [+ residual]); UnaryBlock.forward, blocks.py:493-498."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, contraction):
+    def forward(ctx, x, weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, contraction,
+                nbt=None):
         _lib.require_cuda()
         L = _lib.lib()
         if not x.is_cuda:
@@ -144,7 +146,7 @@ class _LinearBNAct(torch.autograd.Function):
                                             ptr(y), cout, cout, terms, 0, st))
                 ops = (x_hi, x_lo, w_hi, w_lo)
             scale, shift, mean, invstd = _norm_forward(L, y, rows, cout, use_bn, training, gamma, beta, rm, rv,
-                                                       momentum, eps, st)
+                                                       momentum, eps, st, nbt)
             z = torch.empty_like(y)
             check(L.mvk_scale_shift_act(ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res), cout, slope,
                                         ptr(z), cout, None, None, 0, st))
@@ -164,7 +166,7 @@ class _LinearBNAct(torch.autograd.Function):
         batch_stats = 1 if (use_bn and training) else 0
         dx = dw = None
         with torch.cuda.device(dev):
-            sums = torch.zeros(2 * cout, dtype=torch.float64, device=dev)
+            sums = _lib.zeros_f64(2 * cout, dev)
             if has_g or has_b or batch_stats:
                 check(L.mvk_act_bwd_reduce(ptr(g), cout, ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res),
                                            cout, ptr(mean), ptr(invstd), slope, ptr(sums), st))
@@ -209,7 +211,7 @@ class _LinearBNAct(torch.autograd.Function):
                         # dW = dy^T x : both operands stored [K = rows, *] with the M / N index contiguous
                         check(L.mvk_gemm_bf16x3(ptr(dy_hi), ptr(dy_lo), 1, ldh, ptr(x_hi), ptr(x_lo), 1, ldx, cout, cin,
                                                 rows, ptr(dw), cin, cin, terms, split, st))
-        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
 
 
 # -------------------------------------------------------------------------------------------------
@@ -239,16 +241,18 @@ class BatchNormBlock(nn.Module):
                                                                                          str(not self.use_bn))
 
 
-def _tick(bn_module):
-    if bn_module is not None and bn_module.training and bn_module.num_batches_tracked is not None:
-        bn_module.num_batches_tracked += 1
+def _nbt(bn_module, rows):
+    """num_batches_tracked buffer to be incremented inside the statistics kernel (training only)."""
+    if bn_module is not None and bn_module.training and bn_module.num_batches_tracked is not None and rows > 0:
+        return bn_module.num_batches_tracked
+    return None
 
 
 def bn_act(y, bn_block, slope=0.1, residual=None):
     """leaky_relu(bn_block(y) [+ residual], slope); slope = 1 disables the activation."""
     use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(bn_block)
-    _tick(mod)
-    return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope))
+    return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
+                        _nbt(mod, y.shape[0]))
 
 
 class UnaryBlock(nn.Module):
@@ -275,9 +279,8 @@ class UnaryBlock(nn.Module):
         if slope is None:
             slope = 1.0 if self.no_relu else 0.1
         use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(self.batch_norm)
-        _tick(mod)
         return _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps,
-                                  float(slope), self.contraction)
+                                  float(slope), self.contraction, _nbt(mod, x.shape[0]))
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(self.in_dim, self.out_dim,

@@ -109,6 +109,7 @@ struct BnFin {
     float* mean_out;
     float* invstd_out;
     unsigned int* ticket;  // zero-initialised by the caller; NULL = no fused finalize
+    long long* num_batches_tracked;  // optional: += 1 (torch.nn.BatchNorm1d bookkeeping)
 };
 
 __device__ __forceinline__ void bn_finalize_column(const double s0, const double s1, int rows, int c, const BnFin& f) {
@@ -181,6 +182,7 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
         __syncthreads();
         if (s_last) {
             __threadfence();
+            if (threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
             for (int c = threadIdx.x; c < cols; c += TB) {
                 const double s0 = __ldcg(stats + c), s1 = __ldcg(stats + cols + c);
                 bn_finalize_column(s0, s1, rows, c, fin);
@@ -414,13 +416,14 @@ int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk
 
 int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats, const float* gamma,
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                       float* scale, float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream) {
+                       float* scale, float* shift, float* mean_out, float* invstd_out, long long* num_batches_tracked,
+                       mvk_stream_t stream) {
     if (!y || !stats || rows < 1 || cols < 1 || ld < cols || !scale || !shift) return MVK_ERR_INVALID_ARG;
     const int vec = vec_for(cols, ld, 4, 4, 4);
     int grid;
     const int rpc = slab_rows(rows, cols, vec, &grid);
     BnFin fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean_out, invstd_out,
-                 (unsigned int*)(stats + 2 * (size_t)cols)};
+                 (unsigned int*)(stats + 2 * (size_t)cols), num_batches_tracked};
     if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
     else col_stats_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
     MVK_LAUNCHED("col_stats+finalize");

@@ -196,10 +196,12 @@ int mvk_gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B,
  * ---------------------------------------------------------------------------------------------- */
 int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk_stream_t stream);
 /* mvk_col_stats + mvk_bn_finalize(training) in ONE launch: the CTA that retires last converts the
- * sums.  stats must hold 2*cols + 1 zero-initialised doubles (the extra slot is the retirement ticket). */
+ * sums.  stats must hold 2*cols + 1 zero-initialised doubles (the extra slot is the retirement ticket).
+ * num_batches_tracked (device int64, may be NULL) is incremented like torch.nn.BatchNorm1d does. */
 int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats, const float* gamma,
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                       float* scale, float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream);
+                       float* scale, float* shift, float* mean_out, float* invstd_out, long long* num_batches_tracked,
+                       mvk_stream_t stream);
 int mvk_bn_finalize(const double* stats, int rows, int cols, const float* gamma, const float* beta, float eps,
                     float momentum, int training, float* running_mean, float* running_var, float* scale,
                     float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream);
