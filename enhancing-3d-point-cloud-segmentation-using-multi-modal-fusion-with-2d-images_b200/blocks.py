@@ -29,6 +29,25 @@ def _r8(v):
     return (v + 7) // 8 * 8
 
 
+def _attach_hilo(t, hi, lo):
+    """Remember the bf16 hi/lo split of tensor `t` on the tensor object: the next Linear that consumes
+    `t` (UnaryBlock) picks it up instead of re-reading and re-splitting `t`."""
+    try:
+        t._mvk_hilo = (t._version, hi, lo)
+    except Exception:
+        pass
+
+
+def _cached_hilo(t, rows, ld):
+    c = getattr(t, "_mvk_hilo", None)
+    if c is None or c[0] != t._version:
+        return None
+    hi, lo = c[1], c[2]
+    if hi.dim() != 2 or hi.shape[0] != rows or hi.shape[1] != ld or hi.device != t.device:
+        return None
+    return hi, lo
+
+
 def _bn_args(bn_block):
     """(use_bn, gamma, beta_or_bias, running_mean, running_var, momentum, eps, training, module)"""
     if bn_block is None:
@@ -65,7 +84,8 @@ class _BNAct(torch.autograd.Function):
     """z = leaky(bn(y) [+ residual]); blocks.py:446-460 + the activation / residual that follows."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, nbt=None):
+    def forward(ctx, y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, nbt=None,
+                emit_hilo=False):
         _lib.require_cuda()
         L = _lib.lib()
         if not y.is_cuda:
@@ -78,14 +98,23 @@ class _BNAct(torch.autograd.Function):
             scale, shift, mean, invstd = _norm_forward(L, yf, rows, cols, use_bn, training, gamma, beta, rm, rv,
                                                        momentum, eps, st, nbt)
             z = torch.empty_like(yf)
+            hi = lo = None
+            if emit_hilo and cols % 8 == 0:
+                hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=yf.device)
+                lo = torch.empty_like(hi)
             check(L.mvk_scale_shift_act(ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res), cols, slope,
-                                        ptr(z), cols, None, None, 0, st))
+                                        ptr(z), cols, ptr(hi), ptr(lo), cols, st))
         ctx.save_for_backward(yf, scale, shift, mean, invstd, res)
         ctx.cfg = (rows, cols, use_bn, training, slope, gamma is not None, beta is not None)
+        if emit_hilo:
+            if hi is None:
+                hi = lo = torch.empty(0, device=yf.device)
+            ctx.mark_non_differentiable(hi, lo)
+            return z, hi, lo
         return z
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, *_unused):
         L = _lib.lib()
         yf, scale, shift, mean, invstd, res = ctx.saved_tensors
         rows, cols, use_bn, training, slope, has_g, has_b = ctx.cfg
@@ -106,7 +135,7 @@ class _BNAct(torch.autograd.Function):
             check(L.mvk_act_bwd_apply(ptr(g), cols, ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res), cols,
                                       ptr(mean), ptr(invstd), slope, ptr(sums), batch_stats, ptr(dy), cols, None, None,
                                       0, ptr(dres), cols, ptr(dgamma), ptr(dbeta), st))
-        return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None
+        return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
 
 
 class _LinearBNAct(torch.autograd.Function):
@@ -114,7 +143,7 @@ class _LinearBNAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, contraction,
-                nbt=None):
+                nbt=None, emit_hilo=False):
         _lib.require_cuda()
         L = _lib.lib()
         if not x.is_cuda:
@@ -135,11 +164,16 @@ class _LinearBNAct(torch.autograd.Function):
             else:
                 terms = 3 if contraction == "bf16x3" else 1
                 ldx = _r8(cin)
-                x_hi = torch.empty((rows, ldx), dtype=torch.bfloat16, device=dev)
-                x_lo = torch.empty_like(x_hi)
+                cached = _cached_hilo(x, rows, ldx)
+                if cached is not None:
+                    x_hi, x_lo = cached  # produced by the previous block's epilogue or an earlier consumer
+                else:
+                    x_hi = torch.empty((rows, ldx), dtype=torch.bfloat16, device=dev)
+                    x_lo = torch.empty_like(x_hi)
+                    check(L.mvk_split_bf16(ptr(xf), rows, cin, cin, ptr(x_hi), ptr(x_lo), rows, ldx, st))
+                    _attach_hilo(x, x_hi, x_lo)
                 w_hi = torch.empty((cout, ldx), dtype=torch.bfloat16, device=dev)
                 w_lo = torch.empty_like(w_hi)
-                check(L.mvk_split_bf16(ptr(xf), rows, cin, cin, ptr(x_hi), ptr(x_lo), rows, ldx, st))
                 check(L.mvk_split_bf16(ptr(w), cout, cin, cin, ptr(w_hi), ptr(w_lo), cout, ldx, st))
                 if rows > 0:
                     check(L.mvk_gemm_bf16x3(ptr(x_hi), ptr(x_lo), 0, ldx, ptr(w_hi), ptr(w_lo), 0, ldx, rows, cout, cin,
@@ -148,14 +182,23 @@ class _LinearBNAct(torch.autograd.Function):
             scale, shift, mean, invstd = _norm_forward(L, y, rows, cout, use_bn, training, gamma, beta, rm, rv,
                                                        momentum, eps, st, nbt)
             z = torch.empty_like(y)
+            hi = lo = None
+            if emit_hilo and cout % 8 == 0:
+                hi = torch.empty((rows, cout), dtype=torch.bfloat16, device=dev)
+                lo = torch.empty_like(hi)
             check(L.mvk_scale_shift_act(ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res), cout, slope,
-                                        ptr(z), cout, None, None, 0, st))
+                                        ptr(z), cout, ptr(hi), ptr(lo), cout, st))
         ctx.save_for_backward(y, scale, shift, mean, invstd, res, *ops)
         ctx.cfg = (rows, cin, cout, use_bn, training, slope, gamma is not None, beta is not None, contraction)
+        if emit_hilo:
+            if hi is None:
+                hi = lo = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(hi, lo)
+            return z, hi, lo
         return z
 
     @staticmethod
-    def backward(ctx, dz):
+    def backward(ctx, dz, *_unused):
         L = _lib.lib()
         y, scale, shift, mean, invstd, res, *ops = ctx.saved_tensors
         rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction = ctx.cfg
@@ -211,7 +254,7 @@ class _LinearBNAct(torch.autograd.Function):
                         # dW = dy^T x : both operands stored [K = rows, *] with the M / N index contiguous
                         check(L.mvk_gemm_bf16x3(ptr(dy_hi), ptr(dy_lo), 1, ldh, ptr(x_hi), ptr(x_lo), 1, ldx, cout, cin,
                                                 rows, ptr(dw), cin, cin, terms, split, st))
-        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
 
 
 # -------------------------------------------------------------------------------------------------
@@ -248,11 +291,18 @@ def _nbt(bn_module, rows):
     return None
 
 
-def bn_act(y, bn_block, slope=0.1, residual=None):
-    """leaky_relu(bn_block(y) [+ residual], slope); slope = 1 disables the activation."""
+def bn_act(y, bn_block, slope=0.1, residual=None, emit_hilo=False):
+    """leaky_relu(bn_block(y) [+ residual], slope); slope = 1 disables the activation.
+    emit_hilo: also write the result as a bf16 hi/lo pair for a following UnaryBlock (same kernel)."""
     use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(bn_block)
-    return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
-                        _nbt(mod, y.shape[0]))
+    if not emit_hilo:
+        return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
+                            _nbt(mod, y.shape[0]))
+    z, hi, lo = _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
+                             _nbt(mod, y.shape[0]), True)
+    if hi.numel():
+        _attach_hilo(z, hi, lo)
+    return z
 
 
 class UnaryBlock(nn.Module):
@@ -273,14 +323,20 @@ class UnaryBlock(nn.Module):
             self.leaky_relu = nn.LeakyReLU(0.1)
         self.contraction = contraction or _kp.DEFAULT_CONTRACTION
 
-    def forward(self, x, batch=None, residual=None, slope=None):
+    def forward(self, x, batch=None, residual=None, slope=None, emit_hilo=False):
         """x -> leaky_relu(batch_norm(mlp(x))) (blocks.py:493-498).  Extension used by the block
         tail: `residual` is added before the activation and `slope` overrides the block's own."""
         if slope is None:
             slope = 1.0 if self.no_relu else 0.1
         use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(self.batch_norm)
-        return _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps,
-                                  float(slope), self.contraction, _nbt(mod, x.shape[0]))
+        if not emit_hilo:
+            return _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum,
+                                      eps, float(slope), self.contraction, _nbt(mod, x.shape[0]))
+        z, hi, lo = _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum,
+                                       eps, float(slope), self.contraction, _nbt(mod, x.shape[0]), True)
+        if hi.numel():
+            _attach_hilo(z, hi, lo)
+        return z
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(self.in_dim, self.out_dim,

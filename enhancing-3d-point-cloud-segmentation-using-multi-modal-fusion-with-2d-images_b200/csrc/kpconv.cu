@@ -339,8 +339,13 @@ __global__ void __launch_bounds__(256)
 pool_fwd_vec4(const float* __restrict__ x, int ns, int c, const void* __restrict__ inds, int nq, int h,
               int mode, float* __restrict__ out, int* __restrict__ arg) {
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nq; i += gridDim.x * wpb) {
-        for (int ch = lane * 4; ch < c; ch += 128) {
+    const int ncg = (c + 127) / 128;  // work item = (query, group of 128 channels): deep layers have few queries
+    const long long items = (long long)nq * ncg;
+    for (long long it = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); it < items; it += (long long)gridDim.x * wpb) {
+        const int i = (int)(it / ncg);
+        {
+            const int ch = (int)(it % ncg) * 128 + lane * 4;
+            if (ch >= c) continue;
             float4 best = make_float4(0.f, 0.f, 0.f, 0.f);
             int4 bj = make_int4(ns, ns, ns, ns);
             const int hh = mode == 1 ? 1 : h;
@@ -962,6 +967,8 @@ int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, in
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;
     if (c % 4 == 0 && (((size_t)x | (size_t)out | (size_t)arg_out) & 15) == 0) {
+        const long long items = (long long)nq * ((c + 127) / 128);
+        blocks = (int)((items + 7) / 8 < (long long)maxb ? (items + 7) / 8 : maxb);
         if (idx_is_i64)
             pool_fwd_vec4<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
         else

@@ -23,7 +23,7 @@ struct Map2D {
 __host__ __device__ inline Map2D make_map2d(int cols, int vec) {
     Map2D m;
     m.cv = cols / vec;
-    m.cpb = m.cv < TB ? m.cv : TB;
+    m.cpb = m.cv < 32 ? m.cv : 32;  // one CTA covers at most 32 vector columns; blockIdx.y picks the group
     m.rpi = TB / m.cpb;
     return m;
 }
@@ -142,7 +142,7 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
     const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
     const bool active = ty < m.rpi;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-    for (int c0 = 0; c0 < m.cv; c0 += m.cpb) {
+    for (int c0 = blockIdx.y * m.cpb; c0 < m.cv; c0 += m.cpb * gridDim.y) {
         float part[2][VEC];
 #pragma unroll
         for (int e = 0; e < VEC; e++) part[0][e] = part[1][e] = 0.f;
@@ -178,7 +178,7 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
         // the CTA that retires last turns the column sums into scale / shift / running statistics
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0) s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (threadIdx.x == 0) s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x * gridDim.y - 1) ? 1u : 0u;
         __syncthreads();
         if (s_last) {
             __threadfence();
@@ -275,7 +275,7 @@ act_bwd_reduce_kernel(const float* __restrict__ dz, int lddz, const float* __res
     const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
     const bool active = ty < m.rpi;
     const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
-    for (int c0 = 0; c0 < m.cv; c0 += m.cpb) {
+    for (int c0 = blockIdx.y * m.cpb; c0 < m.cv; c0 += m.cpb * gridDim.y) {
         float part[2][VEC];
 #pragma unroll
         for (int e = 0; e < VEC; e++) part[0][e] = part[1][e] = 0.f;
@@ -379,13 +379,15 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int cols,
 inline int vec_for(int cols, int a, int b, int c, int d) {
     return (cols % 4 == 0 && a % 4 == 0 && b % 4 == 0 && c % 4 == 0 && d % 4 == 0) ? 4 : 1;
 }
-inline int slab_rows(int rows, int cols, int vec, int* grid) {
+inline int slab_rows(int rows, int cols, int vec, dim3* grid) {
     Map2D m = make_map2d(cols, vec);
-    int target = num_sms() * 2;  // same-address fp64 atomics serialise in L2: few, fat CTAs
+    const int ncg = (m.cv + m.cpb - 1) / m.cpb;  // column groups (blockIdx.y)
+    int target = num_sms() * 2 / ncg;            // same-address fp64 atomics serialise in L2: few, fat CTAs
+    if (target < 1) target = 1;
     int rpc = (rows + target - 1) / target;
     rpc = (rpc + m.rpi - 1) / m.rpi * m.rpi;
     if (rpc < m.rpi * 4) rpc = m.rpi * 4;
-    *grid = (rows + rpc - 1) / rpc;
+    *grid = dim3((rows + rpc - 1) / rpc, ncg, 1);
     return rpc;
 }
 inline int ew_grid(size_t total) {
@@ -405,7 +407,7 @@ int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk
     if (!y || !stats || rows < 0 || cols < 1 || ld < cols) return MVK_ERR_INVALID_ARG;
     if (rows == 0) return MVK_OK;
     const int vec = vec_for(cols, ld, 4, 4, 4);
-    int grid;
+    dim3 grid;
     const int rpc = slab_rows(rows, cols, vec, &grid);
     BnFin fin = {};
     if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
@@ -420,7 +422,7 @@ int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats
                        mvk_stream_t stream) {
     if (!y || !stats || rows < 1 || cols < 1 || ld < cols || !scale || !shift) return MVK_ERR_INVALID_ARG;
     const int vec = vec_for(cols, ld, 4, 4, 4);
-    int grid;
+    dim3 grid;
     const int rpc = slab_rows(rows, cols, vec, &grid);
     BnFin fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean_out, invstd_out,
                  (unsigned int*)(stats + 2 * (size_t)cols), num_batches_tracked};
@@ -469,7 +471,7 @@ int mvk_act_bwd_reduce(const float* dz, int lddz, const float* y, int rows, int 
         return MVK_ERR_INVALID_ARG;
     if (rows == 0) return MVK_OK;
     const int vec = vec_for(cols, ld, lddz, residual ? ldr : 4, 4);
-    int grid;
+    dim3 grid;
     const int rpc = slab_rows(rows, cols, vec, &grid);
     if (vec == 4)
         act_bwd_reduce_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(dz, lddz, y, rows, cols, ld, scale, shift,

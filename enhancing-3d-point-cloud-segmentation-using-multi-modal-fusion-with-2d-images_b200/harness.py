@@ -88,8 +88,8 @@ class SimpleBlock(nn.Module):
     def forward(self, x, batch):
         q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
         y = self.KPConv(q, s, inds, x)
-        if self.bn_act is not None:
-            return self.bn_act(y, self.batch_norm, slope=0.1)
+        if self.bn_act is not None:  # the output feeds the next block's Linear layers: emit their operand format too
+            return self.bn_act(y, self.batch_norm, slope=0.1, emit_hilo=True)
         return self.leaky_relu(self.batch_norm(y))
 
 
@@ -110,6 +110,7 @@ class ResnetBottleneckBlock(nn.Module):
         self.unary_shortcut = _unary(ops, in_dim, out_dim, bn, mom, no_relu=True) if in_dim != out_dim else nn.Identity()
         self.leaky_relu = nn.LeakyReLU(0.1)
         self.bn_act = getattr(ops, "bn_act", None)
+        self.feeds_linear = True  # cleared by KPFCNN for the block whose output goes to an upsampling
 
     def forward(self, features, batch):
         q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
@@ -117,8 +118,8 @@ class ResnetBottleneckBlock(nn.Module):
         y = self.KPConv(q, s, inds, x)
         shortcut = self.ops.max_pool(features, inds) if 'strided' in self.block_name else features
         if self.bn_act is not None:  # product path: fused bn + act, and bn + residual + act tail
-            x = self.bn_act(y, self.batch_norm_conv, slope=0.1)
-            return self.unary2(x, residual=self.unary_shortcut(shortcut), slope=0.1)
+            x = self.bn_act(y, self.batch_norm_conv, slope=0.1, emit_hilo=True)
+            return self.unary2(x, residual=self.unary_shortcut(shortcut), slope=0.1, emit_hilo=self.feeds_linear)
         x = self.leaky_relu(self.batch_norm_conv(y))
         x = self.unary2(x)
         return self.leaky_relu(x + self.unary_shortcut(shortcut))
@@ -172,6 +173,8 @@ class KPFCNN(nn.Module):
             in_dim = out_dim // 2 if 'simple' in name else out_dim
             if 'pool' in name or 'strided' in name:
                 layer, r, out_dim = layer + 1, r * 2, out_dim * 2
+        if len(self.encoder_blocks) and hasattr(self.encoder_blocks[-1], "feeds_linear"):
+            self.encoder_blocks[-1].feeds_linear = False
         self.decoder_blocks, self.decoder_concats = nn.ModuleList(), []
         for j, name in enumerate(arch[first_up:]):
             if j > 0 and 'upsample' in arch[first_up + j - 1]:
