@@ -34,6 +34,10 @@ SIGNATURES = {
                                   vp, vp, vp, vp]),
     "mvk_kpconv_weighted_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, f32, i32, i32, vp,
                                       i32, vp, vp]),
+    "mvk_kpconv_deform_weighted": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, vp, i32, f32, i32, i32, i32,
+                                         vp, vp, vp, vp, vp, vp]),
+    "mvk_kpconv_deform_weighted_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, vp, i32, f32, i32, i32, vp,
+                                             i32, vp, vp, vp, vp, vp, vp]),
     "mvk_split_bf16": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp]),
     "mvk_gemm_bf16x3": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
     "mvk_gemm_f32": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp, i32, i32, vp]),

@@ -13,8 +13,9 @@ forward  =  stage A  mvk_kpconv_weighted  (neighbour gather + kernel-point influ
 backward =  dA = dOut W^T (same contraction kernel),  dW = A^T dOut (split-K, fp32 atomics),
             dX = scatter of dA through the influences (mvk_kpconv_weighted_bwd, fp32 atomics).
 
-Unsupported reference modes raise instead of silently falling back: deformable / modulated
-KPConv (blocks.py:243-325) is phase 2.
+Deformable / modulated KPConv (blocks.py:243-325): the offsets come from a rigid KPConv of this
+package, the deformed stage A (per-point kernel points, min_d2 for the regulariser, gradients to
+the kernel points and modulations) runs mvk_kpconv_deform_weighted[_bwd].
 """
 import math
 import os
@@ -157,6 +158,120 @@ class _KPConvFunction(torch.autograd.Function):
         return None, None, None, gx, gw, None, None, None, None, None
 
 
+class _KPConvDeformFunction(torch.autograd.Function):
+    """Deformable KPConv (blocks.py:243-374): per-point kernel points `deformed_kp` [N, K, 3] and
+    optional modulations [N, K].  Returns (out [N, Cout], min_d2 [N, K]); gradients flow to x, W,
+    deformed_kp and modulations (and from min_d2 back to deformed_kp for the fitting regulariser)."""
+
+    @staticmethod
+    def forward(ctx, q_pts, s_pts, neighb_inds, x, weights, deformed_kp, modulations, kp_extent, influence,
+                aggregation, contraction):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if not x.is_cuda:
+            raise RuntimeError("KPConv: tensors must live on a CUDA device (no CPU fallback)")
+        q = q_pts.detach().contiguous().float()
+        s = s_pts.detach().contiguous().float()
+        inds, is64 = _idx(neighb_inds)
+        xf = x.detach().contiguous().float()
+        w = weights.detach().contiguous().float()
+        kp = deformed_kp.detach().contiguous().float()
+        mod = None if modulations is None else modulations.detach().contiguous().float()
+        nq, ns, h = q.shape[0], s.shape[0], inds.shape[1]
+        K, cin, cout = w.shape
+        kd = K * cin
+        dev = xf.device
+        out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
+        min_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
+        argmin = torch.empty((nq, K), dtype=torch.int32, device=dev)
+        st = stream_ptr()
+        with torch.cuda.device(dev):
+            if contraction == "fp32":
+                ld = kd
+                A = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                check(L.mvk_kpconv_deform_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin, ptr(kp),
+                                                   ptr(mod), K, float(kp_extent), influence, aggregation, ld, ptr(A),
+                                                   None, None, ptr(min_d2), ptr(argmin), st))
+                if nq > 0:
+                    check(L.mvk_gemm_f32(ptr(A), ld, 1, ptr(w), cout, 1, nq, cout, kd, ptr(out), cout, 1, st))
+                saved = (A,)
+            else:
+                terms = 3 if contraction == "bf16x3" else 1
+                ld, npad = _round_up(kd, 8), _round_up(cout, 8)
+                a_hi = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
+                a_lo = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
+                check(L.mvk_kpconv_deform_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin, ptr(kp),
+                                                   ptr(mod), K, float(kp_extent), influence, aggregation, ld, None,
+                                                   ptr(a_hi), ptr(a_lo), ptr(min_d2), ptr(argmin), st))
+                w_hi = torch.empty((ld, npad), dtype=torch.bfloat16, device=dev)
+                w_lo = torch.empty((ld, npad), dtype=torch.bfloat16, device=dev)
+                check(L.mvk_split_bf16(ptr(w), kd, cout, cout, ptr(w_hi), ptr(w_lo), ld, npad, st))
+                if nq > 0:
+                    check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, ld, ptr(w_hi), ptr(w_lo), 1, npad,
+                                            nq, npad, ld, ptr(out), cout, cout, terms, 0, st))
+                saved = (a_hi, a_lo, w_hi, w_lo)
+        ctx.save_for_backward(q, s, inds, xf, kp, mod if mod is not None else kp.new_empty(0), argmin, w, *saved)
+        ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64, mod is not None)
+        ctx.mark_non_differentiable(argmin)
+        return out, min_d2
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_min_d2):
+        L = _lib.lib()
+        q, s, inds, xf, kp, mod, argmin, w, *saved = ctx.saved_tensors
+        nq, ns, h, K, cin, cout, extent, influence, aggregation, contraction, is64, has_mod = ctx.cfg
+        kd = K * cin
+        dev = grad_out.device
+        go = grad_out.detach().contiguous().float()
+        gmin = None if grad_min_d2 is None else grad_min_d2.detach().contiguous().float()
+        need_x, need_w = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_kp, need_mod = ctx.needs_input_grad[5], ctx.needs_input_grad[6] and has_mod
+        gx = gw = gkp = gmod = None
+        st = stream_ptr()
+        with torch.cuda.device(dev):
+            if contraction == "fp32":
+                (A,) = saved
+                ld = kd
+                if need_w:
+                    gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
+                    if nq > 0:
+                        split = max(1, min(nq // 64, 2 * 148 // max(1, ((kd + 63) // 64) * ((cout + 63) // 64))))
+                        check(L.mvk_gemm_f32(ptr(A), 1, ld, ptr(go), cout, 1, kd, cout, nq, ptr(gw), cout, split, st))
+                dA = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                if nq > 0:
+                    check(L.mvk_gemm_f32(ptr(go), cout, 1, ptr(w), 1, cout, nq, kd, cout, ptr(dA), ld, 1, st))
+            else:
+                a_hi, a_lo, w_hi, w_lo = saved
+                terms = 3 if contraction == "bf16x3" else 1
+                ld, npad = a_hi.shape[1], w_hi.shape[1]
+                go_hi = torch.empty((nq, npad), dtype=torch.bfloat16, device=dev)
+                go_lo = torch.empty((nq, npad), dtype=torch.bfloat16, device=dev)
+                check(L.mvk_split_bf16(ptr(go), nq, cout, cout, ptr(go_hi), ptr(go_lo), nq, npad, st))
+                if need_w:
+                    gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
+                    if nq > 0:
+                        kb_total = (nq + 63) // 64
+                        split = _split_k_for((kd + 127) // 128, (npad + 127) // 128, kb_total)
+                        check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 1, ld, ptr(go_hi), ptr(go_lo), 1, npad,
+                                                kd, npad, nq, ptr(gw), cout, cout, terms, split, st))
+                dA = torch.empty((nq, ld), dtype=torch.float32, device=dev)
+                if nq > 0:
+                    check(L.mvk_gemm_bf16x3(ptr(go_hi), ptr(go_lo), 0, npad, ptr(w_hi), ptr(w_lo), 0, npad,
+                                            nq, ld, npad, ptr(dA), ld, ld, terms, 0, st))
+            if need_x:
+                gx = torch.zeros((ns, cin), dtype=torch.float32, device=dev)
+            if need_kp:
+                gkp = torch.empty((nq, K, 3), dtype=torch.float32, device=dev)
+            if need_mod:
+                gmod = torch.empty((nq, K), dtype=torch.float32, device=dev)
+            if need_x or need_kp or need_mod:
+                check(L.mvk_kpconv_deform_weighted_bwd(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin, ptr(kp),
+                                                       ptr(mod) if has_mod else None, K, extent, influence, aggregation,
+                                                       ptr(dA), ld, ptr(gmin), ptr(argmin), ptr(gx), ptr(gkp), ptr(gmod),
+                                                       st))
+        return None, None, None, gx, gw, gkp, gmod, None, None, None, None
+
+
 class KPConv(nn.Module):
 
     def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
@@ -178,9 +293,10 @@ class KPConv(nn.Module):
         :param contraction: (extension) 'bf16x3' | 'bf16' | 'fp32'; default env MVK_CONTRACTION or 'bf16x3'
         """
         super(KPConv, self).__init__()
-        if deformable or modulated:
-            raise NotImplementedError("deformable / modulated KPConv (blocks.py:243-325) is not implemented "
-                                      "in the B200 path yet; refusing to fall back")
+        if modulated and not deformable:
+            raise ValueError("modulated=True requires deformable=True (blocks.py:187-191)")
+        if deformable and kernel_size > 16:
+            raise NotImplementedError("deformable KPConv supports at most 16 kernel points on the B200 path")
         if p_dim != 3:
             raise NotImplementedError("the B200 path handles 3D point clouds only (p_dim=3)")
         if KP_influence not in _INFLUENCE:
@@ -204,17 +320,26 @@ class KPConv(nn.Module):
         if self.contraction not in CONTRACTIONS:
             raise ValueError("contraction must be one of %r" % (CONTRACTIONS,))
 
-        # Running variables of the deformable branch, kept for attribute compatibility
+        # Running variables of the deformable branch (read by the regulariser, architectures.py:21-54)
         self.min_d2 = None
         self.deformed_KP = None
         self.offset_features = None
-        self.offset_dim = None
-        self.offset_conv = None
-        self.offset_bias = None
 
         # Initialize weights
         self.weights = Parameter(torch.zeros((self.K, in_channels, out_channels), dtype=torch.float32),
                                  requires_grad=True)
+
+        # Offsets come from a rigid KPConv on the same neighbourhoods (blocks.py:186-204)
+        if deformable:
+            self.offset_dim = (self.p_dim + 1) * self.K if modulated else self.p_dim * self.K
+            self.offset_conv = KPConv(self.K, self.p_dim, self.in_channels, self.offset_dim, KP_extent, radius,
+                                      fixed_kernel_points=fixed_kernel_points, KP_influence=KP_influence,
+                                      aggregation_mode=aggregation_mode, contraction=self.contraction)
+            self.offset_bias = Parameter(torch.zeros(self.offset_dim, dtype=torch.float32), requires_grad=True)
+        else:
+            self.offset_dim = None
+            self.offset_conv = None
+            self.offset_bias = None
         self.reset_parameters()
 
         # Initialize kernel points
@@ -222,6 +347,8 @@ class KPConv(nn.Module):
 
     def reset_parameters(self):
         kaiming_uniform_(self.weights, a=math.sqrt(5))
+        if self.deformable:
+            nn.init.zeros_(self.offset_bias)
 
     def init_KP(self):
         """Kernel point positions in a sphere (blocks.py:221-235)."""
@@ -229,6 +356,21 @@ class KPConv(nn.Module):
         return Parameter(torch.tensor(K_points_numpy, dtype=torch.float32), requires_grad=False)
 
     def forward(self, q_pts, s_pts, neighb_inds, x):
+        if self.deformable:
+            # offsets (in units of KP_extent) and modulations from the offset convolution (blocks.py:243-270)
+            self.offset_features = self.offset_conv(q_pts, s_pts, neighb_inds, x) + self.offset_bias
+            if self.modulated:
+                unscaled = self.offset_features[:, :self.p_dim * self.K].reshape(-1, self.K, self.p_dim)
+                modulations = 2 * torch.sigmoid(self.offset_features[:, self.p_dim * self.K:])
+            else:
+                unscaled = self.offset_features.view(-1, self.K, self.p_dim)
+                modulations = None
+            self.deformed_KP = unscaled * self.KP_extent + self.kernel_points
+            out, self.min_d2 = _KPConvDeformFunction.apply(q_pts, s_pts, neighb_inds, x, self.weights, self.deformed_KP,
+                                                           modulations, self.KP_extent,
+                                                           _INFLUENCE[self.KP_influence],
+                                                           _AGGREGATION[self.aggregation_mode], self.contraction)
+            return out
         return _KPConvFunction.apply(q_pts, s_pts, neighb_inds, x, self.weights, self.kernel_points,
                                      self.KP_extent, _INFLUENCE[self.KP_influence],
                                      _AGGREGATION[self.aggregation_mode], self.contraction)

@@ -150,6 +150,25 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
                             int aggregation, const float* grad_weighted, int ld, float* grad_x,
                             mvk_stream_t stream);
 
+/* Deformable KPConv, stage A (blocks.py:243-367): per-point kernel points deformed_kp [nq, K, 3]
+ * (= kernel_points + offsets * KP_extent) and optional modulations [nq, K] (NULL = none), K <= 16.
+ *      weighted[i, k*cin + c] = mod_ik * sum_h w_ihk * x[j_ih, c]
+ *      min_d2[i, k] = min_h ||(s_j - q_i) - kp_ik||^2   (all slots, shadows at 1e6; argmin = its slot)
+ * Neighbours out of range of every kernel point are dropped like the reference's compaction
+ * (:300-325).  Backward: grad_x (+=, caller zeroes; may be NULL), grad_kp [nq, K, 3] and grad_mod
+ * [nq, K] (written; may be NULL); grad_min_d2 (may be NULL) is routed to grad_kp through argmin. */
+int mvk_kpconv_deform_weighted(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                               int idx_is_i64, int h, const float* x, int cin, const float* deformed_kp,
+                               const float* modulations, int num_kp, float kp_extent, int influence, int aggregation,
+                               int ld, float* out_f32, void* out_hi_bf16, void* out_lo_bf16, float* min_d2,
+                               int* argmin, mvk_stream_t stream);
+int mvk_kpconv_deform_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                                   int idx_is_i64, int h, const float* x, int cin, const float* deformed_kp,
+                                   const float* modulations, int num_kp, float kp_extent, int influence,
+                                   int aggregation, const float* grad_weighted, int ld, const float* grad_min_d2,
+                                   const int* argmin, float* grad_x, float* grad_kp, float* grad_mod,
+                                   mvk_stream_t stream);
+
 /* fp32 -> bf16 hi/lo split of a [rows, cols] matrix into zero-padded [rows_pad, ld] buffers. */
 int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, void* lo, int rows_pad,
                    int ld, mvk_stream_t stream);

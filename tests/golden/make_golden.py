@@ -245,6 +245,56 @@ def make_geometry():
     print("geometry.npz", sp.shape, conv.shape, pool.shape, up.shape)
 
 
+def make_kpconv_deformable(blocks):
+    """Deformable / modulated KPConv of the reference (models/blocks.py:243-374): forward, min_d2,
+    deformed_KP and every gradient, with a loss that also pulls on min_d2 like the fitting
+    regulariser does (architectures.py:21-54)."""
+    from oracle import geom
+    rng = np.random.default_rng(4321)
+    flat = {}
+    specs = [
+        # name, n, cin, cout, radius, influence, modulated, strided
+        ("deform_32_64", 500, 32, 64, 0.3, "linear", False, False),
+        ("deform_mod_16_32", 400, 16, 32, 0.3, "linear", True, False),
+        ("deform_strided_64_64", 700, 64, 64, 0.3, "linear", False, True),
+        ("deform_gauss_8_16", 300, 8, 16, 0.3, "gaussian", True, False),
+    ]
+    for name, n, cin, cout, radius, infl, modulated, strided in specs:
+        s_pts = synthetic_cloud(rng, n)
+        lens = np.array([n // 3, n - n // 3], np.int32)
+        if strided:
+            q_pts, q_lens = geom.ref_grid_subsample_batch(s_pts, lens, sampleDl=radius / 2.5 * 2)
+        else:
+            q_pts, q_lens = s_pts, lens
+        inds = geom.ref_batch_neighbors(q_pts, s_pts, q_lens, lens, radius).astype(np.int64)
+        inds = inds[:, :max(4, int(inds.shape[1] * 0.8))]
+        np.random.seed(11)
+        torch.manual_seed(11)
+        extent = radius * 1.2 / 2.5
+        m = blocks.KPConv(15, 3, cin, cout, extent, radius, KP_influence=infl, deformable=True, modulated=modulated)
+        with torch.no_grad():  # non-trivial offsets: the reference initialises the bias with zeros
+            m.offset_bias.uniform_(-0.3, 0.3)
+            m.offset_conv.weights.mul_(0.5)
+        x = torch.randn(len(s_pts), cin).requires_grad_(True)
+        out = m(torch.from_numpy(q_pts), torch.from_numpy(s_pts), torch.from_numpy(inds), x)
+        g = torch.randn_like(out)
+        g2 = torch.randn_like(m.min_d2) * 0.1
+        loss = (out * g).sum() + (m.min_d2 / extent ** 2 * g2).sum()
+        loss.backward()
+        c = dict(q_pts=q_pts, s_pts=s_pts, inds=inds, x=x.detach().numpy(), kernel_points=m.kernel_points.detach().numpy(),
+                 weights=m.weights.detach().numpy(), offset_weights=m.offset_conv.weights.detach().numpy(),
+                 offset_kernel_points=m.offset_conv.kernel_points.detach().numpy(),
+                 offset_bias=m.offset_bias.detach().numpy(), KP_extent=np.float32(extent), radius=np.float32(radius),
+                 influence=np.array(infl), modulated=np.array(modulated), out=out.detach().numpy(),
+                 min_d2=m.min_d2.detach().numpy(), deformed_KP=m.deformed_KP.detach().numpy(), grad_out=g.numpy(),
+                 grad_min_d2=g2.numpy(), grad_x=x.grad.numpy(), grad_w=m.weights.grad.numpy(),
+                 grad_offset_w=m.offset_conv.weights.grad.numpy(), grad_offset_bias=m.offset_bias.grad.numpy())
+        for k, v in c.items():
+            flat[f"{name}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "kpconv_deform.npz"), _versions=_versions(), **flat)
+    print("kpconv_deform.npz", len(flat))
+
+
 def make_blocks(blocks):
     """UnaryBlock / BatchNormBlock of the reference (models/blocks.py:430-504): forward, backward,
     running statistics, in train and eval mode, with and without batch norm."""
@@ -298,6 +348,9 @@ if __name__ == "__main__":
     if only == ["fa"]:
         make_feature_aggregation(import_reference_feature_aggregation())
         sys.exit(0)
+    if only == ["deform"]:
+        make_kpconv_deformable(import_reference_kpconv())
+        sys.exit(0)
     if only == ["blocks"]:
         make_blocks(import_reference_kpconv())
         sys.exit(0)
@@ -308,3 +361,4 @@ if __name__ == "__main__":
     blocks = import_reference_kpconv()
     make_kpconv(blocks)
     make_blocks(blocks)
+    make_kpconv_deformable(blocks)

@@ -76,8 +76,13 @@ def test_kpconv_module_surface(mvk):
     assert np.array_equal(conv.kernel_points.numpy(), g["loaded_seed3_r01"])  # same np.random stream as the reference
     for attr in ("deformable", "min_d2", "deformed_KP", "KP_extent", "K", "radius"):
         assert hasattr(conv, attr)
-    with pytest.raises(NotImplementedError):
-        mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, deformable=True)
+    # deformable: the reference's parameter tree (blocks.py:186-204)
+    d = mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, deformable=True, modulated=True)
+    assert set(d.state_dict()) == {"weights", "kernel_points", "offset_bias", "offset_conv.weights",
+                                   "offset_conv.kernel_points"}
+    assert d.offset_conv.weights.shape == (15, 4, 60) and d.offset_bias.shape == (60,)
+    with pytest.raises(ValueError):
+        mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, modulated=True)
     with pytest.raises(ValueError):
         mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, KP_influence="cubic")
 

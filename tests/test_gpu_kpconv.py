@@ -173,3 +173,39 @@ def test_gemm_tc_against_fp64(mvk):
     D2 = torch.zeros(K, N, device="cuda")
     check(L.mvk_gemm_bf16x3(ptr(at_hi), ptr(at_lo), 1, K, ptr(g_hi), ptr(g_lo), 1, N, K, N, M, ptr(D2), N, N, 3, 4, stream_ptr()))
     assert rel_err(D2, ref2) < 2e-5
+
+
+@pytest.mark.parametrize("contraction", ["fp32", "bf16x3"])
+def test_deformable_kpconv_vs_reference_golden(mvk, contraction):
+    """Deformable / modulated KPConv (blocks.py:243-374) against the reference's own module: output,
+    min_d2, deformed_KP and the gradients of x, W, the offset convolution and the offset bias, with a
+    loss that also pulls on min_d2 (the fitting regulariser's path)."""
+    g = load_golden("kpconv_deform")
+    for name, c in g.items():
+        if name.startswith("_"):
+            continue
+        np.random.seed(0)
+        cin, cout = c["weights"].shape[1:]
+        extent = float(c["KP_extent"])
+        conv = mvk.KPConv(15, 3, cin, cout, extent, float(c["radius"]), KP_influence=str(c["influence"]),
+                          deformable=True, modulated=bool(c["modulated"]), contraction=contraction).cuda()
+        with torch.no_grad():
+            conv.weights.copy_(torch.from_numpy(c["weights"]))
+            conv.kernel_points.copy_(torch.from_numpy(c["kernel_points"]))
+            conv.offset_conv.weights.copy_(torch.from_numpy(c["offset_weights"]))
+            conv.offset_conv.kernel_points.copy_(torch.from_numpy(c["offset_kernel_points"]))
+            conv.offset_bias.copy_(torch.from_numpy(c["offset_bias"]))
+        x = torch.from_numpy(c["x"]).cuda().requires_grad_(True)
+        out = conv(torch.from_numpy(c["q_pts"]).cuda(), torch.from_numpy(c["s_pts"]).cuda(),
+                   torch.from_numpy(c["inds"]).cuda(), x)
+        loss = (out * torch.from_numpy(c["grad_out"]).cuda()).sum() + \
+               (conv.min_d2 / extent ** 2 * torch.from_numpy(c["grad_min_d2"]).cuda()).sum()
+        loss.backward()
+        tol = 1e-4
+        assert rel_err(conv.deformed_KP, c["deformed_KP"]) < tol, (name, "deformed_KP")
+        assert rel_err(conv.min_d2, c["min_d2"]) < tol, (name, "min_d2")
+        assert rel_err(out, c["out"]) < tol, (name, "out")
+        assert rel_err(x.grad, c["grad_x"]) < tol, (name, "grad_x")
+        assert rel_err(conv.weights.grad, c["grad_w"]) < tol, (name, "grad_w")
+        assert rel_err(conv.offset_conv.weights.grad, c["grad_offset_w"]) < 5e-4, (name, "grad_offset_w")
+        assert rel_err(conv.offset_bias.grad, c["grad_offset_bias"]) < 5e-4, (name, "grad_offset_bias")
