@@ -80,7 +80,8 @@ class SimpleBlock(nn.Module):
         self.block_name, self.layer_ind = block_name, layer_ind
         self.KPConv = ops.KPConv(config.num_kernel_points, config.in_points_dim, in_dim, out_dim // 2, extent, radius,
                                  fixed_kernel_points=config.fixed_kernel_points, KP_influence=config.KP_influence,
-                                 aggregation_mode=config.aggregation_mode)
+                                 aggregation_mode=config.aggregation_mode, deformable='deform' in block_name,
+                                 modulated=config.modulated)
         self.batch_norm = _bnblock(ops, out_dim // 2, config.use_batch_norm, config.batch_norm_momentum)
         self.leaky_relu = nn.LeakyReLU(0.1)
         self.bn_act = getattr(ops, "bn_act", None)
@@ -104,7 +105,8 @@ class ResnetBottleneckBlock(nn.Module):
         self.unary1 = _unary(ops, in_dim, out_dim // 4, bn, mom) if in_dim != out_dim // 4 else nn.Identity()
         self.KPConv = ops.KPConv(config.num_kernel_points, config.in_points_dim, out_dim // 4, out_dim // 4, extent,
                                  radius, fixed_kernel_points=config.fixed_kernel_points,
-                                 KP_influence=config.KP_influence, aggregation_mode=config.aggregation_mode)
+                                 KP_influence=config.KP_influence, aggregation_mode=config.aggregation_mode,
+                                 deformable='deform' in block_name, modulated=config.modulated)
         self.batch_norm_conv = _bnblock(ops, out_dim // 4, bn, mom)
         self.unary2 = _unary(ops, out_dim // 4, out_dim, bn, mom, no_relu=True)
         self.unary_shortcut = _unary(ops, in_dim, out_dim, bn, mom, no_relu=True) if in_dim != out_dim else nn.Identity()
@@ -188,6 +190,10 @@ class KPFCNN(nn.Module):
         # NB the reference leaves the LeakyReLU on the logits (architectures.py:296-297)
         self.head_softmax = _unary(ops, config.first_features_dim, self.C, False, 0)
         self.criterion = nn.CrossEntropyLoss(ignore_index=-1)
+        self.K = config.num_kernel_points
+        self.deform_fitting_power = getattr(config, "deform_fitting_power", 1.0)
+        self.repulse_extent = getattr(config, "repulse_extent", 1.2)
+        self.l1 = nn.L1Loss()
 
     def forward(self, batch, config=None):
         x = batch.features.clone().detach()
@@ -203,7 +209,30 @@ class KPFCNN(nn.Module):
         return self.head_softmax(self.head_mlp(x, batch), batch)
 
     def loss(self, outputs, labels):
-        return self.criterion(outputs.transpose(0, 1).unsqueeze(0), labels.unsqueeze(0))
+        loss = self.criterion(outputs.transpose(0, 1).unsqueeze(0), labels.unsqueeze(0))
+        if any(getattr(m, "deformable", False) for m in self.kpconv_layers()):
+            loss = loss + self.fitting_regularizer()
+        return loss
+
+    def fitting_regularizer(self):
+        """Point-to-point fitting + repulsive regulariser of the deformed kernel points
+        (architectures.py:21-54): pulls every deformed kernel point towards its closest input point
+        (min_d2) and pushes kernel points of one neighbourhood apart."""
+        fitting, repulsive = 0, 0
+        for m in self.kpconv_layers():
+            if not getattr(m, "deformable", False):
+                continue
+            d2 = m.min_d2 / (m.KP_extent ** 2)
+            fitting = fitting + self.l1(d2, torch.zeros_like(d2))
+            locs = m.deformed_KP / m.KP_extent
+            for i in range(self.K):
+                other = torch.cat([locs[:, :i, :], locs[:, i + 1:, :]], dim=1).detach()
+                dist = torch.sqrt(torch.sum((other - locs[:, i:i + 1, :]) ** 2, dim=2))
+                rep = torch.sum(torch.clamp_max(dist - self.repulse_extent, max=0.0) ** 2, dim=1)
+                repulsive = repulsive + self.l1(rep, torch.zeros_like(rep)) / self.K
+        return self.deform_fitting_power * (2 * fitting + repulsive)
 
     def kpconv_layers(self):
-        return [m for m in self.modules() if type(m).__name__.startswith("KPConv")]
+        """Top-level KPConv modules (the offset convolutions nested inside deformable ones excluded)."""
+        nested = {id(m.offset_conv) for m in self.modules() if getattr(m, "offset_conv", None) is not None}
+        return [m for m in self.modules() if type(m).__name__.startswith("KPConv") and id(m) not in nested]

@@ -293,8 +293,8 @@ class KPConv(nn.Module):
         :param contraction: (extension) 'bf16x3' | 'bf16' | 'fp32'; default env MVK_CONTRACTION or 'bf16x3'
         """
         super(KPConv, self).__init__()
-        if modulated and not deformable:
-            raise ValueError("modulated=True requires deformable=True (blocks.py:187-191)")
+        # NB like the reference, `modulated` is simply ignored by a rigid layer (blocks.py:186-191):
+        # block_decider passes config.modulated to every KPConv.
         if deformable and kernel_size > 16:
             raise NotImplementedError("deformable KPConv supports at most 16 kernel points on the B200 path")
         if p_dim != 3:

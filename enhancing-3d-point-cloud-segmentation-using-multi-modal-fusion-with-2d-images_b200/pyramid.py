@@ -40,7 +40,8 @@ def baseline_config(**overrides):
         first_subsampling_dl=0.04, conv_radius=2.5, deform_radius=6.0, KP_extent=1.2,
         KP_influence='linear', aggregation_mode='sum', fixed_kernel_points='center', modulated=False,
         first_features_dim=128, in_features_dim=2, use_batch_norm=True, batch_norm_momentum=0.02,
-        in_radius=2.0, num_classes=20, neighborhood_limits=[])
+        in_radius=2.0, num_classes=20, neighborhood_limits=[], deform_fitting_mode='point2point',
+        deform_fitting_power=1.0, repulse_extent=1.2)
     for k, v in overrides.items():
         setattr(cfg, k, v)
     return cfg
@@ -79,18 +80,20 @@ def build_pyramid(stacked_points, stack_lengths, config, ops=None, random_grid_o
             layer_blocks.append(block)
             continue
         level = len(out.points)
-        if any('deformable' in b for b in layer_blocks) or 'deformable' in block:
-            raise NotImplementedError("deformable layers are not supported by the B200 path yet")
+        # deformable layers search a wider neighbourhood (common.py:461-463, 485-487)
+        r_deform = r_normal * config.deform_radius / config.conv_radius
         if layer_blocks:
-            conv_i = nb(stacked_points, stacked_points, stack_lengths, stack_lengths, r_normal, level)
+            r = r_deform if any('deformable' in b for b in layer_blocks) else r_normal
+            conv_i = nb(stacked_points, stacked_points, stack_lengths, stack_lengths, r, level)
         else:
             conv_i = _empty(stacked_points, (0, 1), torch.int32)
         if 'pool' in block or 'strided' in block:
             dl = 2 * r_normal / config.conv_radius
             pool_p, pool_b = ops.batch_grid_subsampling(stacked_points, stack_lengths, sampleDl=dl,
                                                         random_grid_orient=random_grid_orient)
-            pool_i = nb(pool_p, stacked_points, pool_b, stack_lengths, r_normal, level)
-            up_i = nb(stacked_points, pool_p, stack_lengths, pool_b, 2 * r_normal, level + 1)
+            r = r_deform if 'deformable' in block else r_normal
+            pool_i = nb(pool_p, stacked_points, pool_b, stack_lengths, r, level)
+            up_i = nb(stacked_points, pool_p, stack_lengths, pool_b, 2 * r, level + 1)
         else:
             pool_i = _empty(stacked_points, (0, 1), torch.int32)
             pool_p = _empty(stacked_points, (0, 3), torch.float32)

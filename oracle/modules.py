@@ -51,6 +51,49 @@ def kpconv_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_exte
     return torch.sum(kernel_outputs, dim=0)
 
 
+def kpconv_deform_forward(q_pts, s_pts, neighb_inds, x, kernel_points, weights, KP_extent, offset_features,
+                          modulated=False, KP_influence="linear", aggregation_mode="sum"):
+    """Deformable branch (blocks.py:243-374).  `offset_features` [N, K*3 (+K)] is the output of the
+    offset convolution plus bias.  Returns (out, min_d2 [N, K], deformed_KP [N, K, 3]).
+    The reference compacts the neighbours that are in range of some deformed kernel point with a
+    top-k (:300-325); masking the weights of the others is the same computation."""
+    K = kernel_points.shape[0]
+    if modulated:
+        unscaled = offset_features[:, :3 * K].reshape(-1, K, 3)
+        modulations = 2 * torch.sigmoid(offset_features[:, 3 * K:])  # :252-257
+    else:
+        unscaled = offset_features.view(-1, K, 3)
+        modulations = None
+    deformed_KP = unscaled * KP_extent + kernel_points  # :266, :287
+    s_pad = torch.cat((s_pts, torch.zeros_like(s_pts[:1, :]) + 1e6), 0)
+    neighbors = s_pad[neighb_inds, :] - q_pts.unsqueeze(1)
+    differences = neighbors.unsqueeze(2) - deformed_KP.unsqueeze(1)  # [N, H, K, 3]
+    sq_distances = torch.sum(differences ** 2, dim=3)
+    min_d2, _ = torch.min(sq_distances, dim=1)  # :303
+    in_range = torch.any(sq_distances < KP_extent ** 2, dim=2)  # :306  [N, H]
+    if KP_influence == "constant":
+        all_weights = torch.ones_like(sq_distances)
+    elif KP_influence == "linear":
+        all_weights = torch.clamp(1 - torch.sqrt(sq_distances) / KP_extent, min=0.0)
+    elif KP_influence == "gaussian":
+        sigma = KP_extent * 0.3
+        all_weights = torch.exp(-sq_distances / (2 * sigma ** 2 + 1e-9))
+    else:
+        raise ValueError("Unknown influence function type (config.KP_influence)")
+    if aggregation_mode == "closest":
+        nn1 = torch.argmin(sq_distances, dim=2)
+        all_weights = all_weights * F.one_hot(nn1, K).float()
+    all_weights = all_weights * in_range.unsqueeze(2).float()  # dropped neighbours become shadows (:319-323)
+    all_weights = torch.transpose(all_weights, 1, 2)
+    x_pad = torch.cat((x, torch.zeros_like(x[:1, :])), 0)
+    neighb_x = x_pad[neighb_inds]
+    weighted = torch.matmul(all_weights, neighb_x)
+    if modulations is not None:
+        weighted = weighted * modulations.unsqueeze(2)  # :366-367
+    kernel_outputs = torch.matmul(weighted.permute(1, 0, 2), weights)
+    return torch.sum(kernel_outputs, dim=0), min_d2, deformed_KP
+
+
 def max_pool(x, inds):
     """blocks.py:93-110 -- NB pads with ZEROS (not -inf)."""
     x_pad = torch.cat((x, torch.zeros_like(x[:1, :])), 0)
@@ -153,14 +196,26 @@ class KPConvOracle(torch.nn.Module):
         super().__init__()
         import math
         from mvkpconv_b200.kernel_points import load_kernels  # host-side data + RNG mirror only
-        assert not deformable and not modulated
         self.K, self.KP_extent, self.radius = kernel_size, KP_extent, radius
         self.KP_influence, self.aggregation_mode = KP_influence, aggregation_mode
+        self.deformable, self.modulated = deformable, modulated
+        self.min_d2 = self.deformed_KP = None
         self.weights = torch.nn.Parameter(torch.zeros((kernel_size, in_channels, out_channels)))
+        if deformable:  # construction order of blocks.py:186-213 (RNG streams)
+            self.offset_dim = (p_dim + 1) * kernel_size if modulated else p_dim * kernel_size
+            self.offset_conv = KPConvOracle(kernel_size, p_dim, in_channels, self.offset_dim, KP_extent, radius,
+                                            fixed_kernel_points, KP_influence, aggregation_mode)
+            self.offset_bias = torch.nn.Parameter(torch.zeros(self.offset_dim))
         torch.nn.init.kaiming_uniform_(self.weights, a=math.sqrt(5))
         self.kernel_points = torch.nn.Parameter(
             torch.tensor(load_kernels(radius, kernel_size, p_dim, fixed_kernel_points)), requires_grad=False)
 
     def forward(self, q_pts, s_pts, neighb_inds, x):
+        if self.deformable:
+            of = self.offset_conv(q_pts, s_pts, neighb_inds, x) + self.offset_bias
+            out, self.min_d2, self.deformed_KP = kpconv_deform_forward(
+                q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent, of, self.modulated,
+                self.KP_influence, self.aggregation_mode)
+            return out
         return kpconv_forward(q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent,
                               self.KP_influence, self.aggregation_mode)

@@ -81,8 +81,7 @@ def test_kpconv_module_surface(mvk):
     assert set(d.state_dict()) == {"weights", "kernel_points", "offset_bias", "offset_conv.weights",
                                    "offset_conv.kernel_points"}
     assert d.offset_conv.weights.shape == (15, 4, 60) and d.offset_bias.shape == (60,)
-    with pytest.raises(ValueError):
-        mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, modulated=True)
+    assert mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, modulated=True).offset_conv is None  # ignored when rigid, like the reference
     with pytest.raises(ValueError):
         mvk.KPConv(15, 3, 4, 8, 0.05, 0.1, KP_influence="cubic")
 

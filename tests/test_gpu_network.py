@@ -1,0 +1,113 @@
+"""System-level parity on the GPU: the whole hot path (pyramid -> KPFCNN forward -> loss -> backward)
+built from this package's CUDA operators against the same graph built from the CPU oracle
+(reference-order torch KPConv incl. the deformable branch, plain torch unary blocks, oracle C
+geometry).  Covers the block grammar of BASELINE configs 2-4 at a size the oracle runs in seconds:
+rigid and deformable resnet blocks, strided blocks, max-pool shortcuts, nearest upsampling, skip
+concatenation, the fitting regulariser.
+
+Bars: pyramid index matrices bit-exact.  With the strict "fp32" contraction: logits, loss, every
+parameter gradient and the batch-norm running statistics within 1e-4 relative (max-abs / max|ref|;
+measured ~2e-6).  With the default "bf16x3" tensor-core contraction (per-operator error ~1e-5, inside
+the 1e-4 operator budget): logits / loss within 2e-3; gradients are compared as a whole vector
+(relative L2 error < 2e-2) because batch-norm's backward subtracts the column means of the incoming
+gradient, which amplifies the 2^-17 operand rounding of the split-bf16 product by the ratio
+|d| / |d - mean(d)| (measured: worst single tensor ~1e-2 with rigid blocks, median 3e-3)."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import geom, modules
+
+pytestmark = pytest.mark.gpu
+
+ARCH = ['simple', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_deformable', 'resnetb_deformable_strided',
+        'resnetb_deformable', 'nearest_upsample', 'unary', 'nearest_upsample', 'unary']
+
+
+def rel_err(a, b):
+    a = a.detach().double().cpu().numpy()
+    b = b.detach().double().cpu().numpy()
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def cloud(rng, n):
+    xy = rng.uniform(-0.6, 0.6, (n, 2))
+    z = 0.1 * np.sin(5 * xy[:, :1]) * np.cos(3 * xy[:, 1:]) + rng.normal(0, 0.004, (n, 1))
+    return np.concatenate([xy, z], 1).astype(np.float32)
+
+
+@pytest.mark.parametrize("modulated,contraction", [(False, "fp32"), (True, "fp32"), (False, "bf16x3"), (True, "bf16x3")])
+def test_kpfcnn_step_vs_cpu_oracle(mvk, modulated, contraction):
+    from mvkpconv_b200 import harness, pyramid
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([cloud(rng, 1500), cloud(rng, 1200)], 0)
+    lens = np.array([1500, 1200], np.int32)
+    labels = rng.integers(0, 6, len(pts)).astype(np.int64)
+    feats = np.concatenate([np.ones((len(pts), 1), np.float32), pts[:, 2:3]], 1)
+    cfg = pyramid.baseline_config(architecture=list(ARCH), first_subsampling_dl=0.03, first_features_dim=32,
+                                  num_classes=6, in_features_dim=2, modulated=modulated, deform_radius=4.0)
+
+    # ---- CPU oracle graph
+    gops = SimpleNamespace(batch_neighbors=geom.batch_neighbors,
+                           batch_grid_subsampling=lambda p, l, sampleDl=0.1, random_grid_orient=True:
+                           geom.grid_subsample_batch(p, l, sampleDl=sampleDl))
+    mops = SimpleNamespace(KPConv=modules.KPConvOracle, max_pool=modules.max_pool, closest_pool=modules.closest_pool)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net_c = harness.KPFCNN(cfg, ops=mops)
+    sd0 = {k: v.clone() for k, v in net_c.state_dict().items()}  # before the running statistics move
+    pyr_c = pyramid.build_pyramid(pts, lens, cfg, ops=gops, random_grid_orient=False)
+    as_t = lambda lst, dt: [torch.from_numpy(np.ascontiguousarray(a)).to(dt) for a in lst]
+    batch_c = SimpleNamespace(points=as_t(pyr_c.points, torch.float32), neighbors=as_t(pyr_c.neighbors, torch.int64),
+                              pools=as_t(pyr_c.pools, torch.int64), upsamples=as_t(pyr_c.upsamples, torch.int64),
+                              lengths=pyr_c.lengths, features=torch.from_numpy(feats))
+    out_c = net_c(batch_c)
+    loss_c = net_c.loss(out_c, torch.from_numpy(labels))
+    loss_c.backward()
+
+    # ---- product graph on the GPU, same parameters
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net_g = harness.KPFCNN(cfg).cuda()
+    net_g.load_state_dict(sd0, strict=True)
+    for m in net_g.modules():
+        if hasattr(m, "contraction"):
+            m.contraction = contraction
+    dev = torch.device("cuda")
+    pyr_g = pyramid.build_pyramid(torch.from_numpy(pts).to(dev), torch.from_numpy(lens).to(dev), cfg,
+                                  random_grid_orient=False)
+    for name in ("points", "neighbors", "pools", "upsamples"):
+        for lvl, (a, b) in enumerate(zip(getattr(pyr_g, name), getattr(pyr_c, name))):
+            assert np.array_equal(a.cpu().numpy(), np.asarray(b)), (name, lvl)
+    batch_g = SimpleNamespace(points=pyr_g.points, neighbors=pyr_g.neighbors, pools=pyr_g.pools,
+                              upsamples=pyr_g.upsamples, lengths=pyr_g.lengths, features=torch.from_numpy(feats).to(dev))
+    out_g = net_g(batch_g)
+    loss_g = net_g.loss(out_g, torch.from_numpy(labels).to(dev))
+    loss_g.backward()
+
+    strict = contraction == "fp32"
+    tol = 1e-4 if strict else 2e-3
+    assert rel_err(out_g, out_c) < tol
+    assert abs(float(loss_g.detach()) - float(loss_c.detach())) < tol * abs(float(loss_c.detach()))
+    pc, pg = dict(net_c.named_parameters()), dict(net_g.named_parameters())
+    num = den = 0.0
+    checked = 0
+    for k, p in pc.items():
+        if p.grad is None:
+            continue
+        assert pg[k].grad is not None, k
+        d = (pg[k].grad.detach().double().cpu() - p.grad.double())
+        num += float((d * d).sum())
+        den += float((p.grad.double() ** 2).sum())
+        if p.grad.abs().max() > 1e-6:
+            assert rel_err(pg[k].grad, p.grad) < (tol if strict else 0.25), k
+            checked += 1
+    assert checked > 40
+    assert (num / den) ** 0.5 < (1e-4 if strict else 2e-2)
+    # running statistics of the batch-norm layers moved identically
+    bc, bg = dict(net_c.named_buffers()), dict(net_g.named_buffers())
+    for k, b in bc.items():
+        if k.endswith("running_var"):
+            assert rel_err(bg[k], b) < tol, k

@@ -153,3 +153,26 @@ def test_group_points_oracle():
         for n in range(7):
             for k in range(3):
                 assert torch.equal(out[b, :, n, k], p[b, :, idx[b, n, k]])
+
+
+def test_deformable_kpconv_oracle_vs_reference_golden():
+    """The torch restatement of the deformable branch against the reference module's own outputs."""
+    g = load_golden("kpconv_deform")
+    for name, c in g.items():
+        if name.startswith("_"):
+            continue
+        t = lambda k: torch.from_numpy(c[k])
+        x = t("x").requires_grad_(True)
+        w = t("weights").requires_grad_(True)
+        ow = t("offset_weights").requires_grad_(True)
+        ob = t("offset_bias").requires_grad_(True)
+        ext = float(c["KP_extent"])
+        of = modules.kpconv_forward(t("q_pts"), t("s_pts"), t("inds"), x, t("offset_kernel_points"), ow, ext,
+                                    str(c["influence"])) + ob
+        out, min_d2, dkp = modules.kpconv_deform_forward(t("q_pts"), t("s_pts"), t("inds"), x, t("kernel_points"), w,
+                                                         ext, of, bool(c["modulated"]), str(c["influence"]))
+        ((out * t("grad_out")).sum() + (min_d2 / ext ** 2 * t("grad_min_d2")).sum()).backward()
+        close = lambda a, b: np.abs(a.detach().numpy() - b).max() <= 2e-5 * max(np.abs(b).max(), 1e-30)
+        assert close(out, c["out"]) and close(min_d2, c["min_d2"]) and close(dkp, c["deformed_KP"]), name
+        assert close(x.grad, c["grad_x"]) and close(w.grad, c["grad_w"]), name
+        assert close(ow.grad, c["grad_offset_w"]) and close(ob.grad, c["grad_offset_bias"]), name
