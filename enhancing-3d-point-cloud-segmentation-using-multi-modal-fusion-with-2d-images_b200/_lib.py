@@ -164,7 +164,7 @@ class _ZeroPool:
     def take(self, nbytes, device, dtype):
         import torch
         nbytes = (nbytes + 255) // 256 * 256
-        key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+        key = (device.index, torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device()))
         if nbytes > self.CHUNK // 4:
             return torch.zeros(nbytes, dtype=torch.uint8, device=device).view(dtype)
         if self.buf is None or self.key != key or self.off + nbytes > self.CHUNK:
@@ -183,13 +183,34 @@ def zeros_f64(n, device):
 
 
 def stream_ptr():
+    """Raw cudaStream_t of torch's current stream on the current device (as an int for ctypes)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
 def ptr(t):
-    """Device pointer of a (contiguous) torch tensor, or NULL."""
+    """Device pointer of a (contiguous) torch tensor (int), or None (= NULL)."""
     if t is None:
-        return C.c_void_p(0)
+        return None
     assert t.is_contiguous(), "libmvk expects contiguous tensors"
-    return C.c_void_p(t.data_ptr())
+    return t.data_ptr()
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_CTX = _NullCtx()
+
+
+def on_device(device):
+    """Context that makes `device` current -- free when it already is (the common case)."""
+    import torch
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NULL_CTX
+    return torch.cuda.device(device)

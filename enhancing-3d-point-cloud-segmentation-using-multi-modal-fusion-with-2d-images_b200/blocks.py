@@ -94,7 +94,7 @@ class _BNAct(torch.autograd.Function):
         rows, cols = yf.shape
         res = None if residual is None else residual.detach().contiguous().float()
         st = stream_ptr()
-        with torch.cuda.device(yf.device):
+        with _lib.on_device(yf.device):
             scale, shift, mean, invstd = _norm_forward(L, yf, rows, cols, use_bn, training, gamma, beta, rm, rv,
                                                        momentum, eps, st, nbt)
             z = torch.empty_like(yf)
@@ -123,7 +123,7 @@ class _BNAct(torch.autograd.Function):
         st = stream_ptr()
         need_y, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[3]
         batch_stats = 1 if (use_bn and training) else 0
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             sums = _lib.zeros_f64(2 * cols, dev)
             if has_g or has_b or batch_stats:
                 check(L.mvk_act_bwd_reduce(ptr(g), cols, ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res),
@@ -155,7 +155,7 @@ class _LinearBNAct(torch.autograd.Function):
         dev = xf.device
         res = None if residual is None else residual.detach().contiguous().float()
         st = stream_ptr()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             y = torch.empty((rows, cout), dtype=torch.float32, device=dev)
             if contraction == "fp32":
                 if rows > 0:
@@ -208,7 +208,7 @@ class _LinearBNAct(torch.autograd.Function):
         need_x, need_w, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
         batch_stats = 1 if (use_bn and training) else 0
         dx = dw = None
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             sums = _lib.zeros_f64(2 * cout, dev)
             if has_g or has_b or batch_stats:
                 check(L.mvk_act_bwd_reduce(ptr(g), cout, ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res),

@@ -7,6 +7,7 @@ stay on the device).  Failures raise RuntimeError like the CPython extensions do
 (cpp_neighbors/wrapper.cpp:77-205, cpp_subsampling/wrapper.cpp:77-270).
 """
 import ctypes as C
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -60,7 +61,7 @@ def create_3D_rotations(axis, angle):
 
 # -------------------------------------------------------------------------------------------------
 def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbors=None,
-                    out_dtype=torch.int32, return_counts=False):
+                    out_dtype=torch.int32, return_counts=False, deferred=None):
     """Computes neighbors for a batch of queries and supports (datasets/common.py:185-196).
 
     :param queries: (N1, 3) the query points
@@ -73,7 +74,10 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
 
     Extras (not in the reference signature, defaults keep its behaviour): `max_neighbors` crops
     the rows to their nearest entries on the device (== big_neighborhood_filter,
-    common.py:411-421); `out_dtype=torch.int64` emits the dtype the model consumes.
+    common.py:411-421); `out_dtype=torch.int64` emits the dtype the model consumes; `deferred`
+    (a list, with `max_neighbors`) postpones the read-back of the maximum hit count: the call
+    returns without a host sync and appends a check that `resolve_deferred` runs later for all
+    calls at once (it returns the corrected matrices in the rare case a check fails).
     """
     _lib.require_cuda()
     L = _lib.lib()
@@ -90,7 +94,7 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
     if qb.numel() != sb.numel():
         raise RuntimeError("Wrong number of batch elements: different for queries and supports ")
     nq, ns, nb = q.shape[0], s.shape[0], qb.numel()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         wsb = L.mvk_neighbors_workspace_bytes(nq, ns, nb)
         ws = _workspace(wsb, dev)
         counts = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
@@ -103,6 +107,10 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
             check(L.mvk_neighbors_query_capped(ptr(q), nq, ptr(s), ns, ptr(qb), ptr(sb), nb, float(radius), ptr(ws),
                                                ws.numel(), width, cap, ptr(out), 1 if out_dtype == torch.int64 else 0,
                                                ptr(counts), ptr(hmax), stream_ptr()))
+            if deferred is not None and not as_np and not return_counts:
+                args = (queries, supports, q_batches, s_batches, radius, max_neighbors, out_dtype)
+                deferred.append(SimpleNamespace(hmax=hmax, width=width, cap=cap, out=out, args=args))
+                return out
             max_count = int(hmax.item())  # the one host sync
             if max_count < 0:
                 check(-4)
@@ -133,6 +141,28 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
     return (out, counts[:nq]) if return_counts else out
 
 
+def resolve_deferred(records):
+    """One host sync for all deferred neighbour calls.  Returns {index in records: corrected matrix}
+    for the calls whose optimistic single-pass result must be replaced (more hits than the
+    shared-memory lists hold, or fewer hits than the requested width: both rare)."""
+    fixes = {}
+    if not records:
+        return fixes
+    counts = torch.cat([r.hmax for r in records]).cpu().tolist()
+    for i, (r, mc) in enumerate(zip(records, counts)):
+        if mc < 0:
+            check(-4)
+        if mc < 1:
+            raise RuntimeError("Error")  # cpp_neighbors/wrapper.cpp:201-205
+        if mc > r.cap:
+            q, s, qb, sb, radius, lim, dt = r.args
+            full = batch_neighbors(q, s, qb, sb, radius, out_dtype=dt)  # two-phase protocol
+            fixes[i] = full[:, :min(full.shape[1], int(lim))].contiguous()
+        elif mc < r.width:
+            fixes[i] = r.out[:, :mc].contiguous()  # reference width = min(max_count, limit)
+    return fixes
+
+
 def _subsample(points, lengths, features, labels, sampleDl, max_p):
     L = _lib.lib()
     p = _dev(points, torch.float32)
@@ -146,7 +176,7 @@ def _subsample(points, lengths, features, labels, sampleDl, max_p):
     fdim = 0 if f is None else f.shape[1]
     ldim = 0 if l is None else l.shape[1]
     nb = ln.numel()
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         wsb = L.mvk_subsample_workspace_bytes(n, nb, fdim, ldim)
         ws = _workspace(wsb, dev)
         op = torch.empty((max(n, 1), 3), dtype=torch.float32, device=dev)
@@ -220,12 +250,12 @@ def batch_grid_subsampling(points, batches_len, features=None, labels=None, samp
         alpha = np.random.rand(B) * 2 * np.pi
         R = torch.from_numpy(create_3D_rotations(u.T, alpha).astype(np.float32)).contiguous().to(dev)
         rot = torch.empty_like(p)
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(L.mvk_rotate_batch(ptr(p), p.shape[0], ptr(ln), B, ptr(R), 0, ptr(rot), stream_ptr()))
         p = rot
     pts, lens, feats, labs = _subsample(p, ln, features, labels, sampleDl, max_p)
     if random_grid_orient:
         pts = pts.contiguous()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             check(L.mvk_rotate_batch(ptr(pts), pts.shape[0], ptr(lens), B, ptr(R), 1, ptr(pts), stream_ptr()))
     return _pack(as_np, pts, lens, feats, labs, with_len=True)

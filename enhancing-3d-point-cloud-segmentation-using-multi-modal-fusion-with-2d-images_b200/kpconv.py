@@ -73,7 +73,7 @@ class _KPConvFunction(torch.autograd.Function):
         dev = xf.device
         out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
         st = stream_ptr()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             if contraction == "fp32":
                 ld = kd
                 A = torch.empty((nq, ld), dtype=torch.float32, device=dev)
@@ -114,7 +114,7 @@ class _KPConvFunction(torch.autograd.Function):
         need_x, need_w = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         gx = gw = None
         st = stream_ptr()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             if contraction == "fp32":
                 (A,) = saved
                 ld = kd
@@ -185,7 +185,7 @@ class _KPConvDeformFunction(torch.autograd.Function):
         min_d2 = torch.empty((nq, K), dtype=torch.float32, device=dev)
         argmin = torch.empty((nq, K), dtype=torch.int32, device=dev)
         st = stream_ptr()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             if contraction == "fp32":
                 ld = kd
                 A = torch.empty((nq, ld), dtype=torch.float32, device=dev)
@@ -228,7 +228,7 @@ class _KPConvDeformFunction(torch.autograd.Function):
         need_kp, need_mod = ctx.needs_input_grad[5], ctx.needs_input_grad[6] and has_mod
         gx = gw = gkp = gmod = None
         st = stream_ptr()
-        with torch.cuda.device(dev):
+        with _lib.on_device(dev):
             if contraction == "fp32":
                 (A,) = saved
                 ld = kd
@@ -397,7 +397,7 @@ class _PoolFunction(torch.autograd.Function):
         nq, h = ii.shape
         out = torch.empty((nq, c), dtype=torch.float32, device=xf.device)
         arg = torch.empty((nq, c), dtype=torch.int32, device=xf.device) if mode == 0 else None
-        with torch.cuda.device(xf.device):
+        with _lib.on_device(xf.device):
             check(L.mvk_pool(ptr(xf), ns, c, ptr(ii), is64, nq, h, mode, ptr(out), ptr(arg), stream_ptr()))
         ctx.save_for_backward(ii, arg if arg is not None else ii)
         ctx.cfg = (ns, c, nq, h, mode, is64)
@@ -410,7 +410,7 @@ class _PoolFunction(torch.autograd.Function):
         ns, c, nq, h, mode, is64 = ctx.cfg
         go = grad_out.detach().contiguous().float()
         gx = torch.zeros((ns, c), dtype=torch.float32, device=go.device)
-        with torch.cuda.device(go.device):
+        with _lib.on_device(go.device):
             check(L.mvk_pool_bwd(ptr(go), nq, c, ptr(arg) if mode == 0 else None, ptr(ii), is64, h, mode, ns,
                                  ptr(gx), stream_ptr()))
         return gx, None, None

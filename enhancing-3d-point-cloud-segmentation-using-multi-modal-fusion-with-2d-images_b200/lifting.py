@@ -34,7 +34,7 @@ class GroupPointsFunction(torch.autograd.Function):
         b, c, n1 = p.shape
         _, n2, k = idx.shape
         out = torch.empty((b, c, n2, k), dtype=torch.float32, device=p.device)
-        with torch.cuda.device(p.device):
+        with _lib.on_device(p.device):
             check(L.mvk_group_points(ptr(p), b, c, n1, ptr(idx), n2, k, ptr(out), stream_ptr()))
         ctx.save_for_backward(idx)
         ctx.num_points = n1
@@ -47,7 +47,7 @@ class GroupPointsFunction(torch.autograd.Function):
         go = grad_output[0].detach().contiguous().float()
         b, c, n2, k = go.shape
         gi = torch.zeros((b, c, ctx.num_points), dtype=torch.float32, device=go.device)
-        with torch.cuda.device(go.device):
+        with _lib.on_device(go.device):
             check(L.mvk_group_points_bwd(ptr(go), b, c, ctx.num_points, ptr(idx), n2, k, ptr(gi), stream_ptr()))
         return gi, None
 
@@ -228,7 +228,7 @@ def unproject_views(cam_matrix, depths, poses, return_f64=True):
     xyz64 = torch.empty((nv * h * w, 3), dtype=torch.float64, device=dev)
     xyz32 = torch.empty((nv, h, w, 3), dtype=torch.float32, device=dev)
     mask = torch.empty((nv, h, w), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         check(L.mvk_unproject_views(ptr(kinv), ptr(d), ptr(P), nv, h, w, ptr(xyz64), ptr(xyz32), ptr(mask),
                                     stream_ptr()))
     maskb = mask.bool()
@@ -265,7 +265,7 @@ def knn_pixels(xyz64, mask, queries, k=3):
     if int(m.sum().item()) < k:
         raise RuntimeError("knn_pixels: fewer than k valid pixels")
     out = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _lib.on_device(dev):
         wsb = L.mvk_knn_workspace_bytes(npix, nq)
         ws = _workspace(wsb, dev)
         check(L.mvk_knn_pixels(ptr(keys), ptr(m), npix, ptr(q), nq, k, ptr(ws), ws.numel(), ptr(out), stream_ptr()))

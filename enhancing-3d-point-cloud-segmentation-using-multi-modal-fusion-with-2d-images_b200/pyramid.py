@@ -68,9 +68,14 @@ def build_pyramid(stacked_points, stack_lengths, config, ops=None, random_grid_o
     layer_blocks = []
     on_device = isinstance(stacked_points, torch.Tensor)
 
+    deferred = []  # neighbour calls whose max-count read-back is postponed to ONE sync at the end
+    slots = []     # (list, position) of the matrix each deferred call produced
+
     def nb(q, s, ql, sl, r, level):
         lim = limits[level] if level < len(limits) else None
         if on_device:
+            if lim and ops.batch_neighbors is geometry.batch_neighbors:
+                return ops.batch_neighbors(q, s, ql, sl, r, max_neighbors=lim, out_dtype=index_dtype, deferred=deferred)
             return ops.batch_neighbors(q, s, ql, sl, r, max_neighbors=lim, out_dtype=index_dtype)
         res = ops.batch_neighbors(q, s, ql, sl, r)
         return res[:, :lim] if lim else res  # big_neighborhood_filter
@@ -100,15 +105,21 @@ def build_pyramid(stacked_points, stack_lengths, config, ops=None, random_grid_o
             pool_b = _empty(stacked_points, (0,), torch.int32)
             up_i = _empty(stacked_points, (0, 1), torch.int32)
         out.points.append(stacked_points)
-        out.neighbors.append(conv_i)
-        out.pools.append(pool_i)
-        out.upsamples.append(up_i)
+        for lst, mat in ((out.neighbors, conv_i), (out.pools, pool_i), (out.upsamples, up_i)):
+            if any(mat is d.out for d in deferred[len(slots):]):
+                slots.append((lst, len(lst)))
+            lst.append(mat)
         out.lengths.append(stack_lengths)
         stacked_points, stack_lengths = pool_p, pool_b
         r_normal *= 2
         layer_blocks = []
         if 'global' in block or 'upsample' in block:
             break
+    if deferred:
+        assert len(slots) == len(deferred)
+        for i, mat in geometry.resolve_deferred(deferred).items():
+            lst, pos = slots[i]
+            lst[pos] = mat
     return out
 
 
