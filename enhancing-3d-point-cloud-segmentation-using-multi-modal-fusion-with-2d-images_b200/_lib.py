@@ -173,6 +173,16 @@ class _ZeroPool:
         self.off += nbytes
         return out
 
+    def take_ptr(self, nbytes, device):
+        import torch
+        nbytes = (nbytes + 255) // 256 * 256
+        key = (device.index, torch._C._cuda_getCurrentRawStream(device.index if device.index is not None else torch.cuda.current_device()))
+        if self.buf is None or self.key != key or self.off + nbytes > self.buf.numel():
+            self.buf, self.off, self.key = torch.zeros(max(self.CHUNK, nbytes), dtype=torch.uint8, device=device), 0, key
+        p = self.buf.data_ptr() + self.off
+        self.off += nbytes
+        return p
+
 
 _ZEROS = _ZeroPool()
 
@@ -180,6 +190,12 @@ _ZEROS = _ZeroPool()
 def zeros_f64(n, device):
     """n zero-initialised doubles (pooled)."""
     return _ZEROS.take(8 * n, device, __import__("torch").float64)[:n]
+
+
+def zeros_ptr(nbytes, device):
+    """Device pointer of `nbytes` zero-initialised bytes from the pool (no tensor object is created;
+    the memory stays valid for everything enqueued on the current stream: see _ZeroPool)."""
+    return _ZEROS.take_ptr(nbytes, device)
 
 
 def stream_ptr():

@@ -29,23 +29,41 @@ def _r8(v):
     return (v + 7) // 8 * 8
 
 
-def _attach_hilo(t, hi, lo):
+def _carve(device, *sizes):
+    """ONE device allocation carved into 256-byte aligned raw sub-buffers (pointer arithmetic instead
+    of tensor views: creating a tensor object costs as much host time as a small kernel launch).
+    Returns (keep-alive tensor, [device pointer or None for empty sizes, ...])."""
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (int(n) + 255) & ~255
+    t = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+    base = t.data_ptr()
+    return t, [(base + o) if n else None for o, n in zip(offs, sizes)]
+
+
+class _HiLo:
+    """bf16 hi/lo operand pair of an activation tensor, living inside some keep-alive allocation."""
+    __slots__ = ("keep", "hi", "lo", "rows", "ld", "version")
+
+    def __init__(self, keep, hi, lo, rows, ld, version):
+        self.keep, self.hi, self.lo, self.rows, self.ld, self.version = keep, hi, lo, rows, ld, version
+
+
+def _attach_hilo(t, keep, hi, lo, rows, ld):
     """Remember the bf16 hi/lo split of tensor `t` on the tensor object: the next Linear that consumes
     `t` (UnaryBlock) picks it up instead of re-reading and re-splitting `t`."""
     try:
-        t._mvk_hilo = (t._version, hi, lo)
+        t._mvk_hilo = _HiLo(keep, hi, lo, rows, ld, t._version)
     except Exception:
         pass
 
 
 def _cached_hilo(t, rows, ld):
     c = getattr(t, "_mvk_hilo", None)
-    if c is None or c[0] != t._version:
+    if c is None or c.version != t._version or c.rows != rows or c.ld != ld or c.keep.device != t.device:
         return None
-    hi, lo = c[1], c[2]
-    if hi.dim() != 2 or hi.shape[0] != rows or hi.shape[1] != ld or hi.device != t.device:
-        return None
-    return hi, lo
+    return c
 
 
 def _bn_args(bn_block):
@@ -59,25 +77,28 @@ def _bn_args(bn_block):
     return (False, None, bn_block.bias, None, None, 0.0, 0.0, False, None)
 
 
-def _norm_forward(L, y, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st, nbt=None):
-    """-> scale, shift, mean, invstd (device [cols] vectors, None where unused)."""
-    dev = y.device
+def _f32c(t):
+    """fp32 contiguous version of `t` (no new tensor object in the common case)."""
+    if t.dtype is not torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _norm_forward(L, y_ptr, ld, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st, nbt, vec, dev):
+    """Batch-norm bookkeeping of one forward.  `vec` = device pointers [scale, shift, mean, invstd] (each
+    `cols` floats).  Returns the (scale, shift, mean, invstd) pointers the activation kernels use."""
     if not use_bn:
-        return None, (beta.detach().contiguous().float() if beta is not None else None), None, None
-    scale = torch.empty(cols, dtype=torch.float32, device=dev)
-    shift = torch.empty_like(scale)
-    mean = torch.empty_like(scale)
-    invstd = torch.empty_like(scale)
+        return None, (beta.data_ptr() if beta is not None else None), None, None
+    sc, sh, mu, isd = vec
     if training and rows > 0:
         # column sums and, in the CTA that retires last, scale / shift / running statistics: one launch
-        stats = _lib.zeros_f64(2 * cols + 1, dev)
-        check(L.mvk_bn_batch_stats(ptr(y), rows, cols, y.stride(0), ptr(stats), ptr(gamma.detach()), ptr(beta.detach()),
-                                   eps, momentum, ptr(rm), ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
-                                   ptr(nbt), st))
+        stats = _lib.zeros_ptr(8 * (2 * cols + 1), dev)
+        check(L.mvk_bn_batch_stats(y_ptr, rows, cols, ld, stats, gamma.data_ptr(), beta.data_ptr(), eps, momentum,
+                                   ptr(rm), ptr(rv), sc, sh, mu, isd, ptr(nbt), st))
     else:
-        check(L.mvk_bn_finalize(None, rows, cols, ptr(gamma.detach()), ptr(beta.detach()), eps, momentum, 0, ptr(rm),
-                                ptr(rv), ptr(scale), ptr(shift), ptr(mean), ptr(invstd), st))
-    return scale, shift, mean, invstd
+        check(L.mvk_bn_finalize(None, rows, cols, gamma.data_ptr(), beta.data_ptr(), eps, momentum, 0, ptr(rm), ptr(rv),
+                                sc, sh, mu, isd, st))
+    return sc, sh, mu, isd
 
 
 class _BNAct(torch.autograd.Function):
@@ -90,51 +111,48 @@ class _BNAct(torch.autograd.Function):
         L = _lib.lib()
         if not y.is_cuda:
             raise RuntimeError("bn_act: tensors must live on a CUDA device (no CPU fallback)")
-        yf = y.detach().contiguous().float()
+        yf = _f32c(y)
         rows, cols = yf.shape
-        res = None if residual is None else residual.detach().contiguous().float()
+        dev = yf.device
+        res = None if residual is None else _f32c(residual)
+        emit = bool(emit_hilo) and cols % 8 == 0
         st = stream_ptr()
-        with _lib.on_device(yf.device):
-            scale, shift, mean, invstd = _norm_forward(L, yf, rows, cols, use_bn, training, gamma, beta, rm, rv,
-                                                       momentum, eps, st, nbt)
+        with _lib.on_device(dev):
+            keep, (sc, sh, mu, isd, hi, lo) = _carve(dev, *([4 * cols] * 4 if use_bn else [0] * 4),
+                                                      *([2 * rows * cols] * 2 if emit else [0, 0]))
+            sc, sh, mu, isd = _norm_forward(L, yf.data_ptr(), cols, rows, cols, use_bn, training, gamma, beta, rm, rv,
+                                            momentum, eps, st, nbt, (sc, sh, mu, isd), dev)
             z = torch.empty_like(yf)
-            hi = lo = None
-            if emit_hilo and cols % 8 == 0:
-                hi = torch.empty((rows, cols), dtype=torch.bfloat16, device=yf.device)
-                lo = torch.empty_like(hi)
-            check(L.mvk_scale_shift_act(ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res), cols, slope,
-                                        ptr(z), cols, ptr(hi), ptr(lo), cols, st))
-        ctx.save_for_backward(yf, scale, shift, mean, invstd, res)
-        ctx.cfg = (rows, cols, use_bn, training, slope, gamma is not None, beta is not None)
-        if emit_hilo:
-            if hi is None:
-                hi = lo = torch.empty(0, device=yf.device)
-            ctx.mark_non_differentiable(hi, lo)
-            return z, hi, lo
+            check(L.mvk_scale_shift_act(yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols, slope, z.data_ptr(),
+                                        cols, hi, lo, cols, st))
+        ctx.save_for_backward(yf, keep, res, beta if not use_bn else None)
+        ctx.cfg = (rows, cols, use_bn, training, slope, gamma is not None, beta is not None, (sc, sh, mu, isd))
+        if emit:
+            _attach_hilo(z, keep, hi, lo, rows, cols)
         return z
 
     @staticmethod
-    def backward(ctx, dz, *_unused):
+    def backward(ctx, dz):
         L = _lib.lib()
-        yf, scale, shift, mean, invstd, res = ctx.saved_tensors
-        rows, cols, use_bn, training, slope, has_g, has_b = ctx.cfg
-        g = dz.detach().contiguous().float()
+        yf, keep, res, _bias = ctx.saved_tensors
+        rows, cols, use_bn, training, slope, has_g, has_b, (sc, sh, mu, isd) = ctx.cfg
+        g = _f32c(dz)
         dev = g.device
         st = stream_ptr()
         need_y, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[3]
         batch_stats = 1 if (use_bn and training) else 0
         with _lib.on_device(dev):
-            sums = _lib.zeros_f64(2 * cols, dev)
+            sums = _lib.zeros_ptr(16 * cols, dev)
             if has_g or has_b or batch_stats:
-                check(L.mvk_act_bwd_reduce(ptr(g), cols, ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res),
-                                           cols, ptr(mean), ptr(invstd), slope, ptr(sums), st))
+                check(L.mvk_act_bwd_reduce(g.data_ptr(), cols, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols,
+                                           mu, isd, slope, sums, st))
             dy = torch.empty_like(yf) if need_y else None
             dres = torch.empty_like(yf) if (need_res and res is not None) else None
             dgamma = torch.empty(cols, dtype=torch.float32, device=dev) if has_g else None
             dbeta = torch.empty(cols, dtype=torch.float32, device=dev) if has_b else None
-            check(L.mvk_act_bwd_apply(ptr(g), cols, ptr(yf), rows, cols, cols, ptr(scale), ptr(shift), ptr(res), cols,
-                                      ptr(mean), ptr(invstd), slope, ptr(sums), batch_stats, ptr(dy), cols, None, None,
-                                      0, ptr(dres), cols, ptr(dgamma), ptr(dbeta), st))
+            check(L.mvk_act_bwd_apply(g.data_ptr(), cols, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols, mu, isd,
+                                      slope, sums, batch_stats, ptr(dy), cols, None, None, 0, ptr(dres), cols,
+                                      ptr(dgamma), ptr(dbeta), st))
         return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
 
 
@@ -148,112 +166,107 @@ class _LinearBNAct(torch.autograd.Function):
         L = _lib.lib()
         if not x.is_cuda:
             raise RuntimeError("UnaryBlock: tensors must live on a CUDA device (no CPU fallback)")
-        xf = x.detach().contiguous().float()
-        w = weight.detach().contiguous().float()
+        xf = _f32c(x)
+        w = _f32c(weight)
         rows, cin = xf.shape
         cout = w.shape[0]
         dev = xf.device
-        res = None if residual is None else residual.detach().contiguous().float()
+        res = None if residual is None else _f32c(residual)
+        emit = bool(emit_hilo) and cout % 8 == 0
         st = stream_ptr()
+        fp32 = contraction == "fp32"
+        ldx = cin if fp32 else _r8(cin)
+        cached = None if fp32 else _cached_hilo(x, rows, ldx)
         with _lib.on_device(dev):
-            y = torch.empty((rows, cout), dtype=torch.float32, device=dev)
-            if contraction == "fp32":
+            nx = 0 if (fp32 or cached is not None) else 2 * rows * ldx
+            nw = 0 if fp32 else 2 * cout * ldx
+            keep, (x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd, z_hi, z_lo) = _carve(
+                dev, nx, nx, nw, nw, 4 * rows * cout, *([4 * cout] * 4 if use_bn else [0] * 4),
+                *([2 * rows * cout] * 2 if emit else [0, 0]))
+            xkeep = None
+            if fp32:
                 if rows > 0:
-                    check(L.mvk_gemm_f32(ptr(xf), cin, 1, ptr(w), 1, cin, rows, cout, cin, ptr(y), cout, 1, st))
-                ops = (xf, w)
+                    check(L.mvk_gemm_f32(xf.data_ptr(), cin, 1, w.data_ptr(), 1, cin, rows, cout, cin, y, cout, 1, st))
             else:
                 terms = 3 if contraction == "bf16x3" else 1
-                ldx = _r8(cin)
-                cached = _cached_hilo(x, rows, ldx)
                 if cached is not None:
-                    x_hi, x_lo = cached  # produced by the previous block's epilogue or an earlier consumer
+                    x_hi, x_lo, xkeep = cached.hi, cached.lo, cached.keep  # written by the producer's epilogue
                 else:
-                    x_hi = torch.empty((rows, ldx), dtype=torch.bfloat16, device=dev)
-                    x_lo = torch.empty_like(x_hi)
-                    check(L.mvk_split_bf16(ptr(xf), rows, cin, cin, ptr(x_hi), ptr(x_lo), rows, ldx, st))
-                    _attach_hilo(x, x_hi, x_lo)
-                w_hi = torch.empty((cout, ldx), dtype=torch.bfloat16, device=dev)
-                w_lo = torch.empty_like(w_hi)
-                check(L.mvk_split_bf16(ptr(w), cout, cin, cin, ptr(w_hi), ptr(w_lo), cout, ldx, st))
+                    check(L.mvk_split_bf16(xf.data_ptr(), rows, cin, cin, x_hi, x_lo, rows, ldx, st))
+                    _attach_hilo(x, keep, x_hi, x_lo, rows, ldx)
+                check(L.mvk_split_bf16(w.data_ptr(), cout, cin, cin, w_hi, w_lo, cout, ldx, st))
                 if rows > 0:
-                    check(L.mvk_gemm_bf16x3(ptr(x_hi), ptr(x_lo), 0, ldx, ptr(w_hi), ptr(w_lo), 0, ldx, rows, cout, cin,
-                                            ptr(y), cout, cout, terms, 0, st))
-                ops = (x_hi, x_lo, w_hi, w_lo)
-            scale, shift, mean, invstd = _norm_forward(L, y, rows, cout, use_bn, training, gamma, beta, rm, rv,
-                                                       momentum, eps, st, nbt)
-            z = torch.empty_like(y)
-            hi = lo = None
-            if emit_hilo and cout % 8 == 0:
-                hi = torch.empty((rows, cout), dtype=torch.bfloat16, device=dev)
-                lo = torch.empty_like(hi)
-            check(L.mvk_scale_shift_act(ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res), cout, slope,
-                                        ptr(z), cout, ptr(hi), ptr(lo), cout, st))
-        ctx.save_for_backward(y, scale, shift, mean, invstd, res, *ops)
-        ctx.cfg = (rows, cin, cout, use_bn, training, slope, gamma is not None, beta is not None, contraction)
-        if emit_hilo:
-            if hi is None:
-                hi = lo = torch.empty(0, device=dev)
-            ctx.mark_non_differentiable(hi, lo)
-            return z, hi, lo
+                    check(L.mvk_gemm_bf16x3(x_hi, x_lo, 0, ldx, w_hi, w_lo, 0, ldx, rows, cout, cin, y, cout, cout,
+                                            terms, 0, st))
+            sc, sh, mu, isd = _norm_forward(L, y, cout, rows, cout, use_bn, training, gamma, beta, rm, rv, momentum, eps,
+                                            st, nbt, (sc, sh, mu, isd), dev)
+            z = torch.empty((rows, cout), dtype=torch.float32, device=dev)
+            check(L.mvk_scale_shift_act(y, rows, cout, cout, sc, sh, ptr(res), cout, slope, z.data_ptr(), cout, z_hi, z_lo,
+                                        cout, st))
+        ctx.save_for_backward(keep, xkeep, res, xf if fp32 else None, w if fp32 else None, beta if not use_bn else None)
+        ctx.cfg = (rows, cin, cout, use_bn, training, slope, gamma is not None, beta is not None, contraction, ldx,
+                   (x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd))
+        if emit:
+            _attach_hilo(z, keep, z_hi, z_lo, rows, cout)
         return z
 
     @staticmethod
-    def backward(ctx, dz, *_unused):
+    def backward(ctx, dz):
         L = _lib.lib()
-        y, scale, shift, mean, invstd, res, *ops = ctx.saved_tensors
-        rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction = ctx.cfg
-        g = dz.detach().contiguous().float()
+        keep, xkeep, res, xf, w, _bias = ctx.saved_tensors
+        rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction, ldx, ptrs = ctx.cfg
+        x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd = ptrs
+        g = _f32c(dz)
         dev = g.device
         st = stream_ptr()
         need_x, need_w, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
         batch_stats = 1 if (use_bn and training) else 0
         dx = dw = None
         with _lib.on_device(dev):
-            sums = _lib.zeros_f64(2 * cout, dev)
+            sums = _lib.zeros_ptr(16 * cout, dev)
             if has_g or has_b or batch_stats:
-                check(L.mvk_act_bwd_reduce(ptr(g), cout, ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res),
-                                           cout, ptr(mean), ptr(invstd), slope, ptr(sums), st))
-            dres = torch.empty_like(y) if (need_res and res is not None) else None
+                check(L.mvk_act_bwd_reduce(g.data_ptr(), cout, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
+                                           sums, st))
+            dres = torch.empty((rows, cout), dtype=torch.float32, device=dev) if (need_res and res is not None) else None
             dgamma = torch.empty(cout, dtype=torch.float32, device=dev) if has_g else None
             dbeta = torch.empty(cout, dtype=torch.float32, device=dev) if has_b else None
             if contraction == "fp32":
-                xf, w = ops
-                dy = torch.empty_like(y)
-                check(L.mvk_act_bwd_apply(ptr(g), cout, ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res),
-                                          cout, ptr(mean), ptr(invstd), slope, ptr(sums), batch_stats, ptr(dy), cout,
-                                          None, None, 0, ptr(dres), cout, ptr(dgamma), ptr(dbeta), st))
+                dy = torch.empty((rows, cout), dtype=torch.float32, device=dev)
+                check(L.mvk_act_bwd_apply(g.data_ptr(), cout, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
+                                          sums, batch_stats, dy.data_ptr(), cout, None, None, 0, ptr(dres), cout,
+                                          ptr(dgamma), ptr(dbeta), st))
                 if need_x:
                     dx = torch.empty((rows, cin), dtype=torch.float32, device=dev)
                     if rows > 0:
-                        check(L.mvk_gemm_f32(ptr(dy), cout, 1, ptr(w), cin, 1, rows, cin, cout, ptr(dx), cin, 1, st))
+                        check(L.mvk_gemm_f32(dy.data_ptr(), cout, 1, w.data_ptr(), cin, 1, rows, cin, cout, dx.data_ptr(),
+                                             cin, 1, st))
                 if need_w:
                     dw = torch.zeros((cout, cin), dtype=torch.float32, device=dev)
                     if rows > 0:
                         split = max(1, min(rows // 64, 2 * 148 // max(1, ((cout + 63) // 64) * ((cin + 63) // 64))))
-                        check(L.mvk_gemm_f32(ptr(dy), 1, cout, ptr(xf), cin, 1, cout, cin, rows, ptr(dw), cin, split, st))
+                        check(L.mvk_gemm_f32(dy.data_ptr(), 1, cout, xf.data_ptr(), cin, 1, cout, cin, rows, dw.data_ptr(),
+                                             cin, split, st))
             else:
-                x_hi, x_lo, w_hi, w_lo = ops
                 terms = 3 if contraction == "bf16x3" else 1
-                ldx, ldh = x_hi.shape[1], _r8(cout)
-                dy_hi = torch.empty((rows, ldh), dtype=torch.bfloat16, device=dev)
-                dy_lo = torch.empty_like(dy_hi)
-                check(L.mvk_act_bwd_apply(ptr(g), cout, ptr(y), rows, cout, cout, ptr(scale), ptr(shift), ptr(res),
-                                          cout, ptr(mean), ptr(invstd), slope, ptr(sums), batch_stats, None, 0,
-                                          ptr(dy_hi), ptr(dy_lo), ldh, ptr(dres), cout, ptr(dgamma), ptr(dbeta), st))
+                ldh = _r8(cout)
+                dkeep, (dy_hi, dy_lo) = _carve(dev, 2 * rows * ldh, 2 * rows * ldh)
+                check(L.mvk_act_bwd_apply(g.data_ptr(), cout, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
+                                          sums, batch_stats, None, 0, dy_hi, dy_lo, ldh, ptr(dres), cout, ptr(dgamma),
+                                          ptr(dbeta), st))
                 if need_x:
                     dx = torch.empty((rows, cin), dtype=torch.float32, device=dev)
                     if rows > 0:
                         # dx = dy W : A = dy [rows, cout] K-major, B = W stored [K = cout, N = cin] (N contiguous)
-                        check(L.mvk_gemm_bf16x3(ptr(dy_hi), ptr(dy_lo), 0, ldh, ptr(w_hi), ptr(w_lo), 1, ldx, rows, cin,
-                                                cout, ptr(dx), cin, cin, terms, 0, st))
+                        check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 0, ldh, w_hi, w_lo, 1, ldx, rows, cin, cout, dx.data_ptr(),
+                                                cin, cin, terms, 0, st))
                 if need_w:
                     dw = torch.zeros((cout, cin), dtype=torch.float32, device=dev)
                     if rows > 0:
                         kb_total = (rows + 63) // 64
                         split = _kp._split_k_for((cout + 127) // 128, (cin + 127) // 128 if cin > 64 else 1, kb_total)
                         # dW = dy^T x : both operands stored [K = rows, *] with the M / N index contiguous
-                        check(L.mvk_gemm_bf16x3(ptr(dy_hi), ptr(dy_lo), 1, ldh, ptr(x_hi), ptr(x_lo), 1, ldx, cout, cin,
-                                                rows, ptr(dw), cin, cin, terms, split, st))
+                        check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 1, ldh, x_hi, x_lo, 1, ldx, cout, cin, rows, dw.data_ptr(),
+                                                cin, cin, terms, split, st))
         return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
 
 
@@ -295,14 +308,8 @@ def bn_act(y, bn_block, slope=0.1, residual=None, emit_hilo=False):
     """leaky_relu(bn_block(y) [+ residual], slope); slope = 1 disables the activation.
     emit_hilo: also write the result as a bf16 hi/lo pair for a following UnaryBlock (same kernel)."""
     use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(bn_block)
-    if not emit_hilo:
-        return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
-                            _nbt(mod, y.shape[0]))
-    z, hi, lo = _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
-                             _nbt(mod, y.shape[0]), True)
-    if hi.numel():
-        _attach_hilo(z, hi, lo)
-    return z
+    return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
+                        _nbt(mod, y.shape[0]), emit_hilo)
 
 
 class UnaryBlock(nn.Module):
@@ -329,14 +336,8 @@ class UnaryBlock(nn.Module):
         if slope is None:
             slope = 1.0 if self.no_relu else 0.1
         use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(self.batch_norm)
-        if not emit_hilo:
-            return _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum,
-                                      eps, float(slope), self.contraction, _nbt(mod, x.shape[0]))
-        z, hi, lo = _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum,
-                                       eps, float(slope), self.contraction, _nbt(mod, x.shape[0]), True)
-        if hi.numel():
-            _attach_hilo(z, hi, lo)
-        return z
+        return _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps,
+                                  float(slope), self.contraction, _nbt(mod, x.shape[0]), emit_hilo)
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(self.in_dim, self.out_dim,
