@@ -51,6 +51,23 @@ def _split_k_for(m_tiles, n_tiles, kb_total):
     return max(1, min(kb_total, target // max(1, m_tiles * n_tiles)))
 
 
+def _f32c(t):
+    if t.dtype is not torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _carve(device, *sizes):
+    """ONE device allocation carved into 256-byte aligned raw sub-buffers -> (keep-alive tensor, [ptr | None])."""
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (int(n) + 255) & ~255
+    t = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+    base = t.data_ptr()
+    return t, [(base + o) if n else None for o, n in zip(offs, sizes)]
+
+
 class _KPConvFunction(torch.autograd.Function):
     """out[i] = sum_k (sum_h w_ihk x[j_ih]) @ W[k]   (blocks.py:277-374, rigid)."""
 
@@ -61,100 +78,89 @@ class _KPConvFunction(torch.autograd.Function):
         L = _lib.lib()
         if not x.is_cuda:
             raise RuntimeError("KPConv: tensors must live on a CUDA device (no CPU fallback)")
-        q = q_pts.detach().contiguous().float()
-        s = s_pts.detach().contiguous().float()
+        q, s = _f32c(q_pts), _f32c(s_pts)
         inds, is64 = _idx(neighb_inds)
-        xf = x.detach().contiguous().float()
-        w = weights.detach().contiguous().float()
-        kp = kernel_points.detach().contiguous().float()
+        xf, w, kp = _f32c(x), _f32c(weights), _f32c(kernel_points)
         nq, ns, h = q.shape[0], s.shape[0], inds.shape[1]
         K, cin, cout = w.shape
         kd = K * cin
         dev = xf.device
         out = torch.empty((nq, cout), dtype=torch.float32, device=dev)
         st = stream_ptr()
+        fp32 = contraction == "fp32"
         with _lib.on_device(dev):
-            if contraction == "fp32":
-                ld = kd
-                A = torch.empty((nq, ld), dtype=torch.float32, device=dev)
-                check(L.mvk_kpconv_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin,
-                                            ptr(kp), K, float(kp_extent), influence, aggregation, ld,
-                                            ptr(A), None, None, st))
+            if fp32:
+                ld, npad = kd, cout
+                keep, (A, _a, _b, _c) = _carve(dev, 4 * nq * ld, 0, 0, 0)
+                check(L.mvk_kpconv_weighted(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(), cin,
+                                            kp.data_ptr(), K, float(kp_extent), influence, aggregation, ld, A, None, None, st))
                 if nq > 0:
-                    check(L.mvk_gemm_f32(ptr(A), ld, 1, ptr(w), cout, 1, nq, cout, kd, ptr(out), cout, 1, st))
-                saved = (A,)
+                    check(L.mvk_gemm_f32(A, ld, 1, w.data_ptr(), cout, 1, nq, cout, kd, out.data_ptr(), cout, 1, st))
+                ptrs = (A, None, None, None)
             else:
                 terms = 3 if contraction == "bf16x3" else 1
                 ld = _round_up(kd, 8)      # 16-byte row pitch is all TMA needs: partial tiles are zero-filled
                 npad = _round_up(cout, 8)
-                a_hi = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
-                a_lo = torch.empty((nq, ld), dtype=torch.bfloat16, device=dev)
-                check(L.mvk_kpconv_weighted(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, ptr(xf), cin,
-                                            ptr(kp), K, float(kp_extent), influence, aggregation, ld,
-                                            None, ptr(a_hi), ptr(a_lo), st))
-                w_hi = torch.empty((ld, npad), dtype=torch.bfloat16, device=dev)
-                w_lo = torch.empty((ld, npad), dtype=torch.bfloat16, device=dev)
-                check(L.mvk_split_bf16(ptr(w), kd, cout, cout, ptr(w_hi), ptr(w_lo), ld, npad, st))
+                keep, (a_hi, a_lo, w_hi, w_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld, 2 * ld * npad, 2 * ld * npad)
+                check(L.mvk_kpconv_weighted(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(), cin,
+                                            kp.data_ptr(), K, float(kp_extent), influence, aggregation, ld, None, a_hi,
+                                            a_lo, st))
+                check(L.mvk_split_bf16(w.data_ptr(), kd, cout, cout, w_hi, w_lo, ld, npad, st))
                 if nq > 0:
-                    check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 0, ld, ptr(w_hi), ptr(w_lo), 1, npad,
-                                            nq, npad, ld, ptr(out), cout, cout, terms, 0, st))
-                saved = (a_hi, a_lo, w_hi, w_lo)
-        ctx.save_for_backward(q, s, inds, kp, w, *saved)
-        ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64)
+                    check(L.mvk_gemm_bf16x3(a_hi, a_lo, 0, ld, w_hi, w_lo, 1, npad, nq, npad, ld, out.data_ptr(), cout,
+                                            cout, terms, 0, st))
+                ptrs = (a_hi, a_lo, w_hi, w_lo)
+        ctx.save_for_backward(q, s, inds, kp, w, keep)
+        ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64, ld, npad, ptrs)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         L = _lib.lib()
-        q, s, inds, kp, w, *saved = ctx.saved_tensors
-        nq, ns, h, K, cin, cout, extent, influence, aggregation, contraction, is64 = ctx.cfg
+        q, s, inds, kp, w, keep = ctx.saved_tensors
+        nq, ns, h, K, cin, cout, extent, influence, aggregation, contraction, is64, ld, npad, ptrs = ctx.cfg
         kd = K * cin
         dev = grad_out.device
-        go = grad_out.detach().contiguous().float()
+        go = _f32c(grad_out)
         need_x, need_w = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
         gx = gw = None
         st = stream_ptr()
         with _lib.on_device(dev):
             if contraction == "fp32":
-                (A,) = saved
-                ld = kd
+                A = ptrs[0]
+                bkeep, (dA, _g0, _g1) = _carve(dev, 4 * nq * ld if need_x else 0, 0, 0)
                 if need_w:
                     gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
                     if nq > 0:
                         split = max(1, min(nq // 64, 2 * 148 // max(1, ((kd + 63) // 64) * ((cout + 63) // 64))))
                         # dW[kd, cout] = A^T dOut : A'(m, k) = A[k*ld + m]
-                        check(L.mvk_gemm_f32(ptr(A), 1, ld, ptr(go), cout, 1, kd, cout, nq, ptr(gw), cout,
-                                             split, st))
-                if need_x:
-                    dA = torch.empty((nq, ld), dtype=torch.float32, device=dev)
-                    if nq > 0:
-                        # dA[nq, kd] = dOut W^T : B(k=o, n=kd) = W[n*cout + k]
-                        check(L.mvk_gemm_f32(ptr(go), cout, 1, ptr(w), 1, cout, nq, kd, cout, ptr(dA), ld, 1, st))
+                        check(L.mvk_gemm_f32(A, 1, ld, go.data_ptr(), cout, 1, kd, cout, nq, gw.data_ptr(), cout, split, st))
+                if need_x and nq > 0:
+                    # dA[nq, kd] = dOut W^T : B(k=o, n=kd) = W[n*cout + k]
+                    check(L.mvk_gemm_f32(go.data_ptr(), cout, 1, w.data_ptr(), 1, cout, nq, kd, cout, dA, ld, 1, st))
             else:
-                a_hi, a_lo, w_hi, w_lo = saved
+                a_hi, a_lo, w_hi, w_lo = ptrs
                 terms = 3 if contraction == "bf16x3" else 1
-                ld, npad = a_hi.shape[1], w_hi.shape[1]
-                go_hi = torch.empty((nq, npad), dtype=torch.bfloat16, device=dev)
-                go_lo = torch.empty((nq, npad), dtype=torch.bfloat16, device=dev)
-                check(L.mvk_split_bf16(ptr(go), nq, cout, cout, ptr(go_hi), ptr(go_lo), nq, npad, st))
+                bkeep, (dA, go_hi, go_lo) = _carve(dev, 4 * nq * ld if need_x else 0, 2 * nq * npad, 2 * nq * npad)
+                check(L.mvk_split_bf16(go.data_ptr(), nq, cout, cout, go_hi, go_lo, nq, npad, st))
                 if need_w:
                     gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
                     if nq > 0:
                         kb_total = (nq + 63) // 64
-                        split = _split_k_for((kd + 127) // 128, npad // (128 if npad % 128 == 0 else 64), kb_total)
+                        split = _split_k_for((kd + 127) // 128, (npad + 127) // 128, kb_total)
                         # dW = A^T dOut, both operands MN-major, reduction over the points
-                        check(L.mvk_gemm_bf16x3(ptr(a_hi), ptr(a_lo), 1, ld, ptr(go_hi), ptr(go_lo), 1, npad,
-                                                kd, npad, nq, ptr(gw), cout, cout, terms, split, st))
-                if need_x:
-                    dA = torch.empty((nq, ld), dtype=torch.float32, device=dev)
-                    if nq > 0:
-                        # dA = dOut W^T : A = dOut [nq, npad] K-major, B = W [ld, npad] K-major
-                        check(L.mvk_gemm_bf16x3(ptr(go_hi), ptr(go_lo), 0, npad, ptr(w_hi), ptr(w_lo), 0, npad,
-                                                nq, ld, npad, ptr(dA), ld, ld, terms, 0, st))
+                        check(L.mvk_gemm_bf16x3(a_hi, a_lo, 1, ld, go_hi, go_lo, 1, npad, kd, npad, nq, gw.data_ptr(), cout,
+                                                cout, terms, split, st))
+                if need_x and nq > 0:
+                    # dA = dOut W^T : A = dOut [nq, npad] K-major, B = W [ld, npad] K-major
+                    check(L.mvk_gemm_bf16x3(go_hi, go_lo, 0, npad, w_hi, w_lo, 0, npad, nq, ld, npad, dA, ld, ld, terms,
+                                            0, st))
             if need_x:
                 gx = torch.zeros((ns, cin), dtype=torch.float32, device=dev)
-                check(L.mvk_kpconv_weighted_bwd(ptr(q), nq, ptr(s), ns, ptr(inds), is64, h, cin, ptr(kp), K,
-                                                extent, influence, aggregation, ptr(dA), ld, ptr(gx), st))
+                if nq > 0:
+                    check(L.mvk_kpconv_weighted_bwd(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, cin,
+                                                    kp.data_ptr(), K, extent, influence, aggregation, dA, ld, gx.data_ptr(),
+                                                    st))
         return None, None, None, gx, gw, None, None, None, None, None
 
 
