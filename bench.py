@@ -135,7 +135,7 @@ def run_b200(args):
         # gradients live inside the all-reduce buckets (no per-step copy); two buckets for ~97 MB of fp32 gradients
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                           bucket_cap_mb=64)
-    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3)
+    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3, fused=True)
     feats_d, labels_d = feats_p.to(dev), labels_p.to(dev)
     queries_per_step = [0]
     host_enqueue_ms = [0.0]

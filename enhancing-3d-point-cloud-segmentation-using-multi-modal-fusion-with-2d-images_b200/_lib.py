@@ -49,7 +49,7 @@ SIGNATURES = {
     "mvk_act_bwd_apply": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, vp, i32, vp, i32, vp, vp,
                                 i32, vp, i32, vp, vp, vp]),
     "mvk_pool": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
-    "mvk_pool_bwd": (i32, [vp, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
+    "mvk_pool_bwd": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
     "mvk_unproject_views": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "mvk_knn_workspace_bytes": (sz, [i32, i32]),
     "mvk_knn_pixels": (i32, [vp, vp, i32, vp, i32, i32, vp, sz, vp, vp]),

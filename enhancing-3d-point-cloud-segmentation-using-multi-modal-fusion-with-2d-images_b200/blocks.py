@@ -84,6 +84,16 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _rows_f32(t):
+    """(tensor, row pitch) of a 2-D fp32 gradient without copying when only the row pitch is non-trivial
+    (the halves of a torch.cat backward are such views)."""
+    if t.dtype is torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1] and t.stride(0) % 4 == 0 \
+            and t.data_ptr() % 16 == 0:
+        return t, t.stride(0)
+    t = _f32c(t)
+    return t, t.shape[1]
+
+
 def _norm_forward(L, y_ptr, ld, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st, nbt, vec, dev):
     """Batch-norm bookkeeping of one forward.  `vec` = device pointers [scale, shift, mean, invstd] (each
     `cols` floats).  Returns the (scale, shift, mean, invstd) pointers the activation kernels use."""
@@ -136,7 +146,7 @@ class _BNAct(torch.autograd.Function):
         L = _lib.lib()
         yf, keep, res, _bias = ctx.saved_tensors
         rows, cols, use_bn, training, slope, has_g, has_b, (sc, sh, mu, isd) = ctx.cfg
-        g = _f32c(dz)
+        g, ldg = _rows_f32(dz)
         dev = g.device
         st = stream_ptr()
         need_y, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[3]
@@ -144,13 +154,13 @@ class _BNAct(torch.autograd.Function):
         with _lib.on_device(dev):
             sums = _lib.zeros_ptr(16 * cols, dev)
             if has_g or has_b or batch_stats:
-                check(L.mvk_act_bwd_reduce(g.data_ptr(), cols, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols,
+                check(L.mvk_act_bwd_reduce(g.data_ptr(), ldg, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols,
                                            mu, isd, slope, sums, st))
             dy = torch.empty_like(yf) if need_y else None
             dres = torch.empty_like(yf) if (need_res and res is not None) else None
             dgamma = torch.empty(cols, dtype=torch.float32, device=dev) if has_g else None
             dbeta = torch.empty(cols, dtype=torch.float32, device=dev) if has_b else None
-            check(L.mvk_act_bwd_apply(g.data_ptr(), cols, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols, mu, isd,
+            check(L.mvk_act_bwd_apply(g.data_ptr(), ldg, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols, mu, isd,
                                       slope, sums, batch_stats, ptr(dy), cols, None, None, 0, ptr(dres), cols,
                                       ptr(dgamma), ptr(dbeta), st))
         return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
@@ -216,7 +226,7 @@ class _LinearBNAct(torch.autograd.Function):
         keep, xkeep, res, xf, w, _bias = ctx.saved_tensors
         rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction, ldx, ptrs = ctx.cfg
         x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd = ptrs
-        g = _f32c(dz)
+        g, ldg = _rows_f32(dz)
         dev = g.device
         st = stream_ptr()
         need_x, need_w, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
@@ -225,14 +235,14 @@ class _LinearBNAct(torch.autograd.Function):
         with _lib.on_device(dev):
             sums = _lib.zeros_ptr(16 * cout, dev)
             if has_g or has_b or batch_stats:
-                check(L.mvk_act_bwd_reduce(g.data_ptr(), cout, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
+                check(L.mvk_act_bwd_reduce(g.data_ptr(), ldg, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
                                            sums, st))
             dres = torch.empty((rows, cout), dtype=torch.float32, device=dev) if (need_res and res is not None) else None
             dgamma = torch.empty(cout, dtype=torch.float32, device=dev) if has_g else None
             dbeta = torch.empty(cout, dtype=torch.float32, device=dev) if has_b else None
             if contraction == "fp32":
                 dy = torch.empty((rows, cout), dtype=torch.float32, device=dev)
-                check(L.mvk_act_bwd_apply(g.data_ptr(), cout, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
+                check(L.mvk_act_bwd_apply(g.data_ptr(), ldg, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
                                           sums, batch_stats, dy.data_ptr(), cout, None, None, 0, ptr(dres), cout,
                                           ptr(dgamma), ptr(dbeta), st))
                 if need_x:
@@ -250,7 +260,7 @@ class _LinearBNAct(torch.autograd.Function):
                 terms = 3 if contraction == "bf16x3" else 1
                 ldh = _r8(cout)
                 dkeep, (dy_hi, dy_lo) = _carve(dev, 2 * rows * ldh, 2 * rows * ldh)
-                check(L.mvk_act_bwd_apply(g.data_ptr(), cout, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
+                check(L.mvk_act_bwd_apply(g.data_ptr(), ldg, y, rows, cout, cout, sc, sh, ptr(res), cout, mu, isd, slope,
                                           sums, batch_stats, None, 0, dy_hi, dy_lo, ldh, ptr(dres), cout, ptr(dgamma),
                                           ptr(dbeta), st))
                 if need_x:

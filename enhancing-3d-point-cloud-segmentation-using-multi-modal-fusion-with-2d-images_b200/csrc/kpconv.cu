@@ -368,14 +368,14 @@ pool_fwd_vec4(const float* __restrict__ x, int ns, int c, const void* __restrict
 
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-pool_bwd(const float* __restrict__ go, int nq, int c, const int* __restrict__ arg,
+pool_bwd(const float* __restrict__ go, int ldg, int nq, int c, const int* __restrict__ arg,
          const void* __restrict__ inds, int h, int mode, int ns, float* __restrict__ gx) {
     size_t total = (size_t)nq * c;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (size_t)gridDim.x * blockDim.x) {
         int i = (int)(t / c), ch = (int)(t % c);
         int j = mode == 1 ? load_idx<IdxT>(inds, (size_t)i * h) : arg[t];
-        if (j >= 0 && j < ns) atomicAdd(&gx[(size_t)j * c + ch], go[t]);
+        if (j >= 0 && j < ns) atomicAdd(&gx[(size_t)j * c + ch], go[(size_t)i * ldg + ch]);
     }
 }
 
@@ -981,9 +981,9 @@ int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, in
     return MVK_OK;
 }
 
-int mvk_pool_bwd(const float* grad_out, int nq, int c, const int* arg, const void* inds,
+int mvk_pool_bwd(const float* grad_out, int ldg, int nq, int c, const int* arg, const void* inds,
                  int idx_is_i64, int h, int mode, int ns, float* grad_x, mvk_stream_t stream) {
-    if (!grad_out || !grad_x || c < 1 || nq < 0 || (mode == 0 && !arg) || (mode == 1 && !inds))
+    if (!grad_out || !grad_x || c < 1 || ldg < c || nq < 0 || (mode == 0 && !arg) || (mode == 1 && !inds))
         return MVK_ERR_INVALID_ARG;
     if (nq == 0) return MVK_OK;
     size_t total = (size_t)nq * c;
@@ -991,9 +991,9 @@ int mvk_pool_bwd(const float* grad_out, int nq, int c, const int* arg, const voi
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;
     if (idx_is_i64)
-        pool_bwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, nq, c, arg, inds, h, mode, ns, grad_x);
+        pool_bwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ldg, nq, c, arg, inds, h, mode, ns, grad_x);
     else
-        pool_bwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, nq, c, arg, inds, h, mode, ns, grad_x);
+        pool_bwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ldg, nq, c, arg, inds, h, mode, ns, grad_x);
     MVK_LAUNCHED("pool_bwd");
     return MVK_OK;
 }

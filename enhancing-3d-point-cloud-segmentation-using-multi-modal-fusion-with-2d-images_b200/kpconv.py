@@ -414,11 +414,13 @@ class _PoolFunction(torch.autograd.Function):
         L = _lib.lib()
         ii, arg = ctx.saved_tensors
         ns, c, nq, h, mode, is64 = ctx.cfg
-        go = grad_out.detach().contiguous().float()
+        go = grad_out
+        if not (go.dtype is torch.float32 and go.dim() == 2 and go.stride(1) == 1 and go.stride(0) >= c):
+            go = _f32c(go)  # otherwise only the row pitch differs (a half of a torch.cat backward): no copy
         gx = torch.zeros((ns, c), dtype=torch.float32, device=go.device)
         with _lib.on_device(go.device):
-            check(L.mvk_pool_bwd(ptr(go), nq, c, ptr(arg) if mode == 0 else None, ptr(ii), is64, h, mode, ns,
-                                 ptr(gx), stream_ptr()))
+            check(L.mvk_pool_bwd(go.data_ptr(), go.stride(0), nq, c, ptr(arg) if mode == 0 else None, ptr(ii), is64, h,
+                                 mode, ns, ptr(gx), stream_ptr()))
         return gx, None, None
 
 

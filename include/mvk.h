@@ -241,8 +241,8 @@ int mvk_act_bwd_apply(const float* dz, int lddz, const float* y, int rows, int c
  * winning support row for the backward.  Backward: grad_x[arg] += grad_out. */
 int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, int nq, int h, int mode,
              float* out, int* arg_out, mvk_stream_t stream);
-int mvk_pool_bwd(const float* grad_out, int nq, int c, const int* arg, const void* inds,
-                 int idx_is_i64, int h, int mode, int ns, float* grad_x, mvk_stream_t stream);
+int mvk_pool_bwd(const float* grad_out, int ldg /* row pitch of grad_out, >= c */, int nq, int c, const int* arg,
+                 const void* inds, int idx_is_i64, int h, int mode, int ns, float* grad_x, mvk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 2D -> 3D lifting.
