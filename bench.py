@@ -66,7 +66,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.p = None
@@ -228,17 +228,17 @@ def run_b200(args):
             ob = 4 if terms == 3 else 2  # bytes per operand element (hi + lo, or hi only)
             return ("contraction", f"[M={M},N={N},K={K},amn={a[2]},bmn={a[6]},split={a[15]}]",
                     ob * (M * K + K * N) + 4.0 * M * nv, 2.0 * M * N * K * terms)
-        if name == "mvk_col_stats":
-            return "bn_stream", f"[{a[1]}x{a[2]}]", 4.0 * a[1] * a[2], 0.0
+        if name in ("mvk_col_stats", "mvk_bn_batch_stats"):
+            return "bn_stats", f"[{a[1]}x{a[2]}]", 4.0 * a[1] * a[2], 0.0
         if name == "mvk_scale_shift_act":
-            return "bn_stream", f"[{a[1]}x{a[2]}]", 4.0 * a[1] * a[2] * (2 + nz(a[6])), 0.0
+            return "bn_act_fwd", f"[{a[1]}x{a[2]}]", 4.0 * a[1] * a[2] * (2 + nz(a[6]) + nz(a[11])), 0.0
         if name == "mvk_act_bwd_reduce":
-            return "bn_stream", f"[{a[3]}x{a[4]}]", 4.0 * a[3] * a[4] * (2 + nz(a[8])), 0.0
+            return "bn_act_bwd_reduce", f"[{a[3]}x{a[4]}]", 4.0 * a[3] * a[4] * (2 + nz(a[8])), 0.0
         if name == "mvk_act_bwd_apply":
             n = a[3] * a[4]
-            return "bn_stream", f"[{a[3]}x{a[4]}]", 4.0 * n * (3 + nz(a[8]) + nz(a[20])), 0.0
+            return "bn_act_bwd_apply", f"[{a[3]}x{a[4]}]", 4.0 * n * (3 + nz(a[8]) + nz(a[20])), 0.0
         if name == "mvk_split_bf16":
-            return "bn_stream", f"[{a[1]}x{a[2]}]", 8.0 * a[1] * a[2], 0.0
+            return "operand_split", f"[{a[1]}x{a[2]}]", 8.0 * a[1] * a[2], 0.0
         if name in ("mvk_neighbors_query_capped",):
             nq, ns, width, is64 = a[1], a[3], a[10], a[13]
             return "neighbors", "", nq * 12.0 + ns * 12.0 + nq * width * (8 if is64 else 4), 0.0
@@ -280,10 +280,22 @@ def run_b200(args):
                 "frac_of_mixed_roofline": round(f["ideal_ms"] / f["ms"], 4)}
 
     KERNEL_OF = {"stage_a_fwd": "kp_fwd_fast / kp_fwd_tiny (mvk_kpconv_weighted)", "stage_a_bwd": "kp_bwd_fast (mvk_kpconv_weighted_bwd)",
-                 "contraction": "gemm_tc_kernel (mvk_gemm_bf16x3)", "bn_stream": "col_stats / scale_shift_act / act_bwd_* / split_bf16"}
+                 "contraction": "gemm_tc_kernel (mvk_gemm_bf16x3)", "bn_stats": "col_stats_kernel (mvk_bn_batch_stats)",
+                 "bn_act_fwd": "scale_shift_act_kernel (mvk_scale_shift_act)", "bn_act_bwd_reduce": "act_bwd_reduce_kernel",
+                 "bn_act_bwd_apply": "act_bwd_apply_kernel", "operand_split": "split_bf16_vec4 (mvk_split_bf16)",
+                 "neighbors": "k_query (mvk_neighbors_query_capped)"}
     rooflines = {k: roof(KERNEL_OF.get(k, k), f) for k, f in fam.items() if f["bytes"] > 0 or f["flops"] > 0}
     top = max(rooflines.items(), key=lambda kv: fam[kv[0]]["ms"], default=(None, None))
     roofline = top[1]
+    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/), if any
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if roofline is not None and top[0] in tr:
+            roofline["traffic"] = tr[top[0]]["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tr[top[0]]["source"]
+            roofline["algorithmic_bytes_per_launch"] = round(fam[top[0]]["bytes"] / fam[top[0]]["calls"], 1)
+    except Exception:
+        pass
     breakdown = {n: {"ms_per_step": round(v[0] / args.steps, 3), "calls_per_step": v[1] // args.steps}
                  for n, v in sorted(by_entry.items(), key=lambda kv: -kv[1][0])}
     nb_ms = sum(v[0] for n, v in by_entry.items() if n.startswith("mvk_neighbors"))

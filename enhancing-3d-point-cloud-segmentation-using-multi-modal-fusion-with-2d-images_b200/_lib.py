@@ -40,10 +40,11 @@ SIGNATURES = {
                                              i32, vp, vp, vp, vp, vp, vp]),
     "mvk_split_bf16": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp]),
     "mvk_gemm_bf16x3": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
+    "mvk_gemm_bf16x3_stats": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp]),
     "mvk_gemm_f32": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp, i32, i32, vp]),
     "mvk_col_stats": (i32, [vp, i32, i32, i32, vp, vp]),
     "mvk_bn_batch_stats": (i32, [vp, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "mvk_bn_finalize": (i32, [vp, i32, i32, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "mvk_bn_finalize": (i32, [vp, i32, i32, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "mvk_scale_shift_act": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, f32, vp, i32, vp, vp, i32, vp]),
     "mvk_act_bwd_reduce": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, vp, vp]),
     "mvk_act_bwd_apply": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, vp, i32, vp, i32, vp, vp,

@@ -16,6 +16,8 @@ writes the pre-activation gradient directly in the contraction's operand format.
 
 No CPU fallback: tensors must be CUDA tensors.
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
@@ -23,6 +25,9 @@ from torch.nn.parameter import Parameter
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 from . import kpconv as _kp
+
+
+_FUSE_BN_STATS = os.environ.get("MVK_FUSE_BN_STATS", "0") == "1"
 
 
 def _r8(v):
@@ -94,20 +99,25 @@ def _rows_f32(t):
     return t, t.shape[1]
 
 
-def _norm_forward(L, y_ptr, ld, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st, nbt, vec, dev):
+def _norm_forward(L, y_ptr, ld, rows, cols, use_bn, training, gamma, beta, rm, rv, momentum, eps, st, nbt, vec, dev,
+                  stats=None):
     """Batch-norm bookkeeping of one forward.  `vec` = device pointers [scale, shift, mean, invstd] (each
     `cols` floats).  Returns the (scale, shift, mean, invstd) pointers the activation kernels use."""
     if not use_bn:
         return None, (beta.data_ptr() if beta is not None else None), None, None
     sc, sh, mu, isd = vec
-    if training and rows > 0:
+    if training and rows > 0 and stats is not None:
+        # the column sums came out of the contraction's epilogue: only the [cols]-sized bookkeeping is left
+        check(L.mvk_bn_finalize(stats, rows, cols, gamma.data_ptr(), beta.data_ptr(), eps, momentum, 1, ptr(rm), ptr(rv),
+                                sc, sh, mu, isd, ptr(nbt), st))
+    elif training and rows > 0:
         # column sums and, in the CTA that retires last, scale / shift / running statistics: one launch
         stats = _lib.zeros_ptr(8 * (2 * cols + 1), dev)
         check(L.mvk_bn_batch_stats(y_ptr, rows, cols, ld, stats, gamma.data_ptr(), beta.data_ptr(), eps, momentum,
                                    ptr(rm), ptr(rv), sc, sh, mu, isd, ptr(nbt), st))
     else:
         check(L.mvk_bn_finalize(None, rows, cols, gamma.data_ptr(), beta.data_ptr(), eps, momentum, 0, ptr(rm), ptr(rv),
-                                sc, sh, mu, isd, st))
+                                sc, sh, mu, isd, None, st))
     return sc, sh, mu, isd
 
 
@@ -193,7 +203,7 @@ class _LinearBNAct(torch.autograd.Function):
             keep, (x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd, z_hi, z_lo) = _carve(
                 dev, nx, nx, nw, nw, 4 * rows * cout, *([4 * cout] * 4 if use_bn else [0] * 4),
                 *([2 * rows * cout] * 2 if emit else [0, 0]))
-            xkeep = None
+            xkeep = stats = None
             if fp32:
                 if rows > 0:
                     check(L.mvk_gemm_f32(xf.data_ptr(), cin, 1, w.data_ptr(), 1, cin, rows, cout, cin, y, cout, 1, st))
@@ -205,11 +215,17 @@ class _LinearBNAct(torch.autograd.Function):
                     check(L.mvk_split_bf16(xf.data_ptr(), rows, cin, cin, x_hi, x_lo, rows, ldx, st))
                     _attach_hilo(x, keep, x_hi, x_lo, rows, ldx)
                 check(L.mvk_split_bf16(w.data_ptr(), cout, cin, cin, w_hi, w_lo, cout, ldx, st))
-                if rows > 0:
+                if rows > 0 and use_bn and training and _FUSE_BN_STATS:
+                    # batch statistics ride in the contraction's epilogue (measured: the extra epilogue work
+                    # costs as much as the separate statistics pass it saves, so this is off by default)
+                    stats = _lib.zeros_ptr(16 * cout, dev)
+                    check(L.mvk_gemm_bf16x3_stats(x_hi, x_lo, 0, ldx, w_hi, w_lo, 0, ldx, rows, cout, cin, y, cout, cout,
+                                                  terms, 0, stats, st))
+                elif rows > 0:
                     check(L.mvk_gemm_bf16x3(x_hi, x_lo, 0, ldx, w_hi, w_lo, 0, ldx, rows, cout, cin, y, cout, cout,
                                             terms, 0, st))
             sc, sh, mu, isd = _norm_forward(L, y, cout, rows, cout, use_bn, training, gamma, beta, rm, rv, momentum, eps,
-                                            st, nbt, (sc, sh, mu, isd), dev)
+                                            st, nbt, (sc, sh, mu, isd), dev, stats)
             z = torch.empty((rows, cout), dtype=torch.float32, device=dev)
             check(L.mvk_scale_shift_act(y, rows, cout, cout, sc, sh, ptr(res), cout, slope, z.data_ptr(), cout, z_hi, z_lo,
                                         cout, st))

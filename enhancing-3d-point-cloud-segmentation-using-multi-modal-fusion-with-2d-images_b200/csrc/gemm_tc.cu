@@ -30,12 +30,14 @@ constexpr int MAX_STAGES = 8;
 constexpr int A_TILE_BYTES = 16384;            // 128 rows x 128 B (one of hi / lo)
 constexpr int MAX_THREADS = 320;               // 2 + up to 8 epilogue warps
 constexpr int STAGING_PER_WARP = 2 * 4096;     // 2 buffers x [32 rows x 128 B] per epilogue warp
+constexpr int COLSUM_BYTES = 4 * 2 * 256 * 4;  // per epilogue warp: {sum, sum of squares} x 256 columns
 constexpr int SMEM_LIMIT = 232448;             // 227 KB opt-in maximum per CTA
 
 struct GemmParams {
     float* D;
     int M, N, ldd, bn, kb_total, kb_per_split, splits, terms, a_mn, b_mn, atomic_out, stages, tma_store;
     int m_tiles, n_tiles, num_tiles, tmem_cols, stage_bytes, ew, d_swizzle;
+    double* col_stats;  // optional [2 * N]: column sums / sums of squares of D (batch-norm statistics), fp64 atomics
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -290,6 +292,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         const int quarter = warp & 3;
         const int nhalf = p.ew >> 2, half = (warp - 2) >> 2;
         const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (uint32_t)STAGING_PER_WARP;
+        // fused batch-norm statistics: warp-private column partials [2][256] behind the staging tiles
+        float* colsum = (float*)(smem_dyn + (staging - smem_u32(smem_dyn)) + p.ew * STAGING_PER_WARP) + quarter * 512;
+        const bool stats_on = p.col_stats != nullptr;
+        if (stats_on)
+            for (int c = lane; c < 512; c += 32) colsum[c] = 0.f;
         int it = 0;
         int sbuf = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
@@ -346,6 +353,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
                         tma_store_2d(&tm_d, tile, n0 + c0, m0, p.atomic_out);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
+                    if (stats_on) {
+                        // lane = column of the chunk: sum this warp's 32 rows from the staging tile (for a fixed
+                        // row the 32 lanes read one swizzled 128-byte line: conflict-free); rows past M are zero
+                        float s0 = 0.f, s1 = 0.f;
+                        const uint32_t col_off = (uint32_t)((lane & 3) << 2);
+#pragma unroll 8
+                        for (int r = 0; r < 32; r++) {
+                            const int rr = quarter * 32 + r;
+                            const uint32_t addr = tile + (uint32_t)rr * 128u + (uint32_t)((((lane >> 2) ^ (rr & 7))) << 4) + col_off;
+                            float x;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+                            s0 += x;
+                            s1 = fmaf(x, x, s1);
+                        }
+                        colsum[c0 + lane] += s0;
+                        colsum[256 + c0 + lane] += s1;
+                    }
                     sbuf ^= 1;
                 } else if (row < p.M) {
                     float* dst = p.D + (size_t)row * p.ldd + n0 + c0;
@@ -365,6 +389,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
             if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
         }
         if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (stats_on) {
+            // four warp-private partial vectors -> one fp64 atomic per column, statistic and CTA
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const float* all = colsum - quarter * 512;
+            for (int c = (warp - 2) * 32 + lane; c < p.N; c += 128) {
+                const float t0 = all[c] + all[512 + c] + all[1024 + c] + all[1536 + c];
+                const float t1 = all[256 + c] + all[768 + c] + all[1280 + c] + all[1792 + c];
+                atomicAdd(p.col_stats + c, (double)t0);
+                atomicAdd(p.col_stats + p.N + c, (double)t1);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -435,9 +470,11 @@ int choose_bn(int N, bool b_mn, int max_bn) {
 
 using namespace mvk;
 
-extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
-                               const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
-                               int n_valid, int terms, int split_k, mvk_stream_t stream) {
+extern "C" int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk_stream_t stream);
+
+static int gemm_impl(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
+                     const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
+                     int n_valid, int terms, int split_k, double* col_stats, mvk_stream_t stream) {
     if (!a_hi || !b_hi || !D || M < 1 || N < 1 || K < 1 || (lda % 8) != 0 || (ldb % 8) != 0 ||
         n_valid < 1 || n_valid > N || ldd < n_valid || (terms != 1 && terms != 3))
         return MVK_ERR_INVALID_ARG;
@@ -489,8 +526,14 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * p.bn) p.tmem_cols <<= 1;
     p.stage_bytes = 2 * A_TILE_BYTES + 2 * p.bn * 128;
-    const int staging_bytes = p.ew * STAGING_PER_WARP;
+    int staging_bytes = p.ew * STAGING_PER_WARP;
     p.stages = (SMEM_LIMIT - 2048 - staging_bytes) / p.stage_bytes;  // 1 KB alignment slack + static smem
+    bool stats_fit = false;
+    if (col_stats) {  // the column partials need 8 KB more: only if that does not cost a pipeline stage
+        const int with = (SMEM_LIMIT - 2048 - staging_bytes - COLSUM_BYTES) / p.stage_bytes;
+        stats_fit = with >= (p.stages < MAX_STAGES ? p.stages : MAX_STAGES);
+        if (stats_fit) staging_bytes += COLSUM_BYTES;
+    }
     if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
     p.tma_store = ((ldd % 4) == 0 && (((size_t)D) & 15) == 0) ? 1 : 0;
     // output row pitch not a multiple of 16 bytes: fragment-layout epilogue (8-byte sector-exact stores)
@@ -522,6 +565,10 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
         if ((rc = make_map(&mb_hi, b_hi, N, K, ldb, 64, 64))) return rc;
         if ((rc = make_map(&mb_lo, bl, N, K, ldb, 64, 64))) return rc;
     }
+    // statistics ride in the TMA-store epilogue of unsplit, single-column-tile problems; otherwise a
+    // separate pass over D below
+    p.col_stats = (col_stats && stats_fit && p.tma_store == 1 && p.splits == 1 && p.n_tiles == 1 && n_valid <= 256)
+                      ? col_stats : nullptr;
     if (p.tma_store == 1) {
         p.d_swizzle = 1;
         if ((rc = make_map(&md, D, n_valid, M, ldd, 32, 128, 4, p.d_swizzle != 0))) return rc;
@@ -536,5 +583,21 @@ extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_majo
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
     gemm_tc_kernel<<<grid, 64 + 32 * p.ew, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
     MVK_LAUNCHED("gemm_tc_kernel");
+    if (col_stats && !p.col_stats) return mvk_col_stats(D, M, n_valid, ldd, col_stats, stream);
     return MVK_OK;
+}
+
+extern "C" int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
+                               const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
+                               int n_valid, int terms, int split_k, mvk_stream_t stream) {
+    return gemm_impl(a_hi, a_lo, a_mn_major, lda, b_hi, b_lo, b_mn_major, ldb, M, N, K, D, ldd, n_valid, terms, split_k,
+                     nullptr, stream);
+}
+
+extern "C" int mvk_gemm_bf16x3_stats(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
+                                     const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
+                                     int n_valid, int terms, int split_k, double* col_stats, mvk_stream_t stream) {
+    if (!col_stats) return MVK_ERR_INVALID_ARG;
+    return gemm_impl(a_hi, a_lo, a_mn_major, lda, b_hi, b_lo, b_mn_major, ldb, M, N, K, D, ldd, n_valid, terms, split_k,
+                     col_stats, stream);
 }

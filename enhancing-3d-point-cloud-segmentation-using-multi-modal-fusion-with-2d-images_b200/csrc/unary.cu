@@ -199,7 +199,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int rows, i
                                    const float* __restrict__ beta, float eps, float momentum, int training,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ invstd_out) {
+                                   float* __restrict__ invstd_out, long long* __restrict__ num_batches_tracked) {
+    if (num_batches_tracked && blockIdx.x == 0 && threadIdx.x == 0) *num_batches_tracked += 1;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cols; c += gridDim.x * blockDim.x) {
         float mean, invstd;
         if (training) {
@@ -434,12 +435,13 @@ int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats
 
 int mvk_bn_finalize(const double* stats, int rows, int cols, const float* gamma, const float* beta, float eps,
                     float momentum, int training, float* running_mean, float* running_var, float* scale,
-                    float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream) {
+                    float* shift, float* mean_out, float* invstd_out, long long* num_batches_tracked,
+                    mvk_stream_t stream) {
     if (cols < 1 || !scale || !shift || (training && !stats) || (!training && (!running_mean || !running_var)))
         return MVK_ERR_INVALID_ARG;
     bn_finalize_kernel<<<(cols + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         stats, rows, cols, gamma, beta, eps, momentum, training, running_mean, running_var, scale, shift, mean_out,
-        invstd_out);
+        invstd_out, training ? num_batches_tracked : nullptr);
     MVK_LAUNCHED("bn_finalize");
     return MVK_OK;
 }

@@ -187,6 +187,13 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
 int mvk_gemm_bf16x3(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
                     const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
                     int n_valid, int terms, int split_k, mvk_stream_t stream);
+/* Same contraction, additionally accumulating the column sums and sums of squares of D into
+ * col_stats[0:n_valid] / col_stats[n_valid:2 n_valid] (fp64, zero-initialised by the caller) -- the
+ * batch statistics of a following batch norm.  Unsplit single-column-tile problems fold this into
+ * the epilogue (no extra pass over D); other shapes run mvk_col_stats afterwards. */
+int mvk_gemm_bf16x3_stats(const void* a_hi, const void* a_lo, int a_mn_major, int lda, const void* b_hi,
+                          const void* b_lo, int b_mn_major, int ldb, int M, int N, int K, float* D, int ldd,
+                          int n_valid, int terms, int split_k, double* col_stats, mvk_stream_t stream);
 /* Strict fp32 SIMT contraction with arbitrary strides:
  *      D[m, n] (+)= sum_k A[m*a_rs + k*a_cs] * B[k*b_rs + n*b_cs]                                */
 int mvk_gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B, long long b_rs,
@@ -223,7 +230,8 @@ int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats
                        mvk_stream_t stream);
 int mvk_bn_finalize(const double* stats, int rows, int cols, const float* gamma, const float* beta, float eps,
                     float momentum, int training, float* running_mean, float* running_var, float* scale,
-                    float* shift, float* mean_out, float* invstd_out, mvk_stream_t stream);
+                    float* shift, float* mean_out, float* invstd_out, long long* num_batches_tracked /* may be NULL */,
+                    mvk_stream_t stream);
 int mvk_scale_shift_act(const float* y, int rows, int cols, int ld, const float* scale, const float* shift,
                         const float* residual, int ldr, float slope, float* out, int ldo, void* out_hi_bf16,
                         void* out_lo_bf16, int ldh, mvk_stream_t stream);

@@ -28,3 +28,8 @@ if [ "$WHAT" = "full" ] || [ "$WHAT" = "all" ]; then
   done
 fi
 du -sh gpurun_out; ls -la gpurun_out | tail -12
+if [ "$WHAT" = "traffic" ]; then
+  # DRAM bytes of every contraction launch of one step (feeds profiles/traffic.json)
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:gemm_tc -s ${SKIP_GEMM:-470} -c 152 --csv --log-file gpurun_out/gemm_traffic_$TAG.csv $CMD > gpurun_out/ncu_traffic_$TAG.log 2>&1
+  echo "traffic rc=$?"
+fi

@@ -111,3 +111,24 @@ def test_bn_act_and_residual_tail_vs_torch(mvk):
     z19.backward(torch.ones_like(z19))
     assert rel_err(bb.bias.grad, torch.full((19,), 777.0)) < 1e-6
     assert rel_err(y19.grad, torch.ones_like(y19)) < 1e-6
+
+
+def test_gemm_fused_column_statistics(mvk):
+    """mvk_gemm_bf16x3_stats: column sums / sums of squares out of the contraction's epilogue (and the
+    fallback pass for split problems) against torch."""
+    L = mvk._lib.lib()
+    from mvkpconv_b200._lib import check, ptr, stream_ptr
+    torch.manual_seed(1)
+    for (M, N, K) in [(5000, 128, 64), (3000, 32, 96), (700, 512, 256), (129, 64, 4096)]:
+        A = torch.randn(M, K, device="cuda")
+        B = torch.randn(N, K, device="cuda")
+        hi = lambda t: t.bfloat16()
+        lo = lambda t: (t - t.bfloat16().float()).bfloat16()
+        D = torch.zeros(M, N, device="cuda")
+        stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+        check(L.mvk_gemm_bf16x3_stats(ptr(hi(A)), ptr(lo(A)), 0, K, ptr(hi(B)), ptr(lo(B)), 0, K, M, N, K, ptr(D), N, N, 3, 0,
+                                      ptr(stats), stream_ptr()))
+        ref = A.double() @ B.double().t()
+        assert rel_err(D, ref) < 2e-5
+        assert rel_err(stats[:N], ref.sum(0)) < 1e-4, (M, N, K)
+        assert rel_err(stats[N:], (ref * ref).sum(0)) < 1e-4, (M, N, K)
