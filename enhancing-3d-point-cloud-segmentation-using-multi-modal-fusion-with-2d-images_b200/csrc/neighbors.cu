@@ -135,8 +135,9 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
-    float* l_d2 = (float*)smem_raw + (size_t)wib * list_cap * 2;
-    int* l_idx = (int*)(l_d2 + list_cap);
+    // hit list of this warp: one 64-bit key per hit = (d2 bits << 32) | support index.  d2 >= 0, so the
+    // unsigned order of the keys IS the reference order (d2 ascending, index ascending on exact ties)
+    unsigned long long* l_key = (unsigned long long*)smem_raw + (size_t)wib * list_cap;
     const unsigned int mask = g.cap - 1;
     const int nq_valid = min(nq, g.q_starts[nb]);
     if (*g.err != 0) {  // a support fell outside the indexable cell range: report, do nothing
@@ -187,10 +188,8 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
                 unsigned int m = __ballot_sync(0xffffffffu, hit);
                 if (WRITE && hit) {
                     int pos = nfound + __popc(m & ((1u << lane) - 1));
-                    if (pos < list_cap) {
-                        l_d2[pos] = d2;
-                        l_idx[pos] = idx;
-                    }
+                    if (pos < list_cap)
+                        l_key[pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)idx;
                 }
                 nfound += __popc(m);
             }
@@ -208,16 +207,17 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
             __syncwarp();
             int n = min(nfound, list_cap);
             OutT* row = out + (size_t)i * width;
+            if ((n & 1) && lane == 0 && n < list_cap) l_key[n] = 0xFFFFFFFFFFFFFFFFull;  // pad to an even count
+            __syncwarp();
+            const int n2 = (n + 1) & ~1;
             for (int e = lane; e < n; e += 32) {
-                float de = l_d2[e];
-                int ie = l_idx[e];
+                const unsigned long long my = l_key[e];
                 int rank = 0;
-                for (int f = 0; f < n; f++) {
-                    float df = l_d2[f];
-                    int jf = l_idx[f];
-                    rank += (df < de || (df == de && jf < ie)) ? 1 : 0;
+                for (int f = 0; f < n2; f += 2) {  // two keys per 128-bit shared load (warp-wide broadcast)
+                    const ulonglong2 kk = *(const ulonglong2*)(l_key + f);
+                    rank += (kk.x < my ? 1 : 0) + (kk.y < my ? 1 : 0);
                 }
-                if (rank < width) row[rank] = (OutT)ie;
+                if (rank < width) row[rank] = (OutT)(unsigned int)(my & 0xFFFFFFFFull);
             }
             for (int p = n + lane; p < width; p += 32) row[p] = (OutT)ns;
             __syncwarp();
