@@ -109,7 +109,19 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to fd 1 when the communicator is created; stdout must carry
+        # exactly ONE JSON line, so park fd 1 on stderr while the process group comes up
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     L = _lib.lib()
 
     # ---------------- synthetic batch of this rank (host side, untimed) ----------------
@@ -131,14 +143,30 @@ def run_b200(args):
     for m in net.kpconv_layers():
         m.contraction = args.contraction
     model = net
-    if world > 1:
+    use_ddp = world > 1 and args.allreduce == "ddp"
+    if use_ddp:
         # gradients live inside the all-reduce buckets (no per-step copy); two buckets for ~97 MB of fp32 gradients
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                           bucket_cap_mb=64)
+    elif world > 1:
+        # identical replicas to start with (DDP would broadcast rank 0's parameters and buffers)
+        for t in list(net.parameters()) + list(net.buffers()):
+            dist.broadcast(t.data, 0)
+    grad_params = [p for p in net.parameters() if p.requires_grad]
+
+    def allreduce_grads():
+        """Gradient averaging without DDP's buckets: ONE coalesced NCCL all-reduce over the per-parameter
+        gradient tensors right after backward (no flatten / copy-back, no per-parameter hooks)."""
+        grads = [p.grad for p in grad_params if p.grad is not None]
+        with dist._coalescing_manager(device=dev, async_ops=False):
+            for g in grads:
+                dist.all_reduce(g)
+        torch._foreach_div_(grads, float(world))
     opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3, fused=True)
     feats_d, labels_d = feats_p.to(dev), labels_p.to(dev)
     queries_per_step = [0]
     host_enqueue_ms = [0.0]
+    per_rank = []
 
     def step(from_host):
         if from_host:
@@ -157,6 +185,8 @@ def run_b200(args):
         loss = net.loss(out, y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
+        if world > 1 and not use_ddp:
+            allreduce_grads()
         torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)  # utils/trainer.py:191-193
         opt.step()
         return loss.item() if from_host else loss
@@ -185,13 +215,16 @@ def run_b200(args):
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            mine = torch.tensor([ms, float(n_pts)], device=dev)
+            allr = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allr, mine)
+            per_rank[:] = [(round(float(a[0]) / steps, 3), int(a[1])) for a in allr]
+            ms = max(float(a[0]) for a in allr)  # the job is as slow as its slowest rank
         return ms, L.mvk_launch_count() - l0, clocks, float(last)
 
     ms, launches, clocks, loss_v = timed(False, args.steps, args.warmup, sample_clocks=True)
     enqueue_ms = host_enqueue_ms[0]
+    ranks_info = list(per_rank)
     if args.quick:  # profiling runs (ncu): only the device-resident timed region
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": round(ms / args.steps, 3), "points": n_pts,
@@ -317,7 +350,7 @@ def run_b200(args):
                                    "layers, 24.4M params) pyramid + fwd + bwd + SGD, 8 synthetic spheres/GPU",
                        "spheres_per_gpu": SPHERES_PER_GPU, "points_per_gpu": n_pts, "in_radius": IN_RADIUS,
                        "first_subsampling_dl": FIRST_DL, "K": 15, "neighborhood_limits": cfg.neighborhood_limits,
-                       "parallelism": f"sphere-sharded x{world}, DDP grad all-reduce" if world > 1 else "single GPU",
+                       "parallelism": (f"sphere-sharded x{world}, gradient all-reduce (NCCL, {args.allreduce})" if world > 1 else "single GPU"),
                        "l2": "per-step working set (saved [N,15*Cin] operands, >1 GB) far exceeds the 126 MB L2; no flush"},
             "e2e": {"value": round(total_pts * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d),
@@ -327,6 +360,8 @@ def run_b200(args):
             "neighbor_queries_per_step": int(queries_per_step[0]),
             "breakdown_ms": breakdown, "loss": loss_v, "host_enqueue_ms_per_step": round(enqueue_ms, 3),
         }
+        if ranks_info:
+            line["per_rank_ms_and_points"] = ranks_info
         if args.detail:
             det = sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.detail]
             line["detail_us_per_call"] = {k: [round(1e3 * v[0] / v[1], 1), v[1] // args.steps] for k, v in det}
@@ -435,6 +470,8 @@ def main():
     ap.add_argument("--contraction", default=os.environ.get("MVK_CONTRACTION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allreduce", default="coalesced", choices=["coalesced", "ddp"],
+                    help="N > 1: one coalesced NCCL all-reduce of the gradients after backward, or torch DDP buckets")
     ap.add_argument("--detail", type=int, default=0, help="add the N most expensive (entry point, shape) rows")
     ap.add_argument("--quick", action="store_true", help="device-resident timed region only (for ncu runs)")
     args = ap.parse_args()

@@ -31,7 +31,7 @@ def _digest():
     files = sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
         os.path.join(os.path.dirname(HERE), "include", "mvk.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())  # NOT the absolute path: the repo is copied to other roots (GPU box)
         h.update(open(f, "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()
@@ -52,16 +52,29 @@ def build(force=False, verbose=False):
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("libmvk.so is missing/stale and nvcc was not found: cannot build the CUDA path")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-        print(" ".join(cmd))
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    open(STAMP, "w").write(_digest())
+    # several ranks may import the package at once: serialise the build and publish the library atomically
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():
+                return LIB  # another process built it while we waited
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc] + NVCC_FLAGS + ["-o", tmp] + sources()
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+                print(" ".join(cmd))
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+            os.replace(tmp, LIB)
+            open(STAMP, "w").write(_digest())
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
