@@ -163,3 +163,49 @@ def test_subsampling_properties_at_scale(mvk):
     fwd = set(zip(i[:200000].tolist(), j[:200000].tolist()))
     allp = set(zip(i.tolist(), j.tolist()))
     assert all((b, a) in allp for a, b in fwd)
+
+
+def test_scene_sweep_geometry_at_full_size(mvk):
+    """BASELINE config 5 size: a 200k-point synthetic scene, multi-level grid subsampling + radius
+    search at every level.  Full-size checks through size-independent properties (rows sorted by
+    d2, strict radius, shadow padding, symmetry of the relation, idempotent subsampling) plus exact
+    agreement with the oracle on a random subset of the query rows of every level."""
+    from mvkpconv_b200 import synthetic
+    room = synthetic.make_room(seed=3, density=5200.0, size=(8.0, 6.0, 2.8), n_boxes=12)
+    pts = mvk.grid_subsampling(room, sampleDl=0.04)
+    assert 150_000 < len(pts) < 300_000
+    rng = np.random.default_rng(0)
+    radius, dl = 0.1, 0.08
+    for level in range(4):
+        n = len(pts)
+        lens = np.array([n], np.int32)
+        inds, counts = mvk.batch_neighbors(pts, pts, lens, lens, radius, return_counts=True)
+        assert inds.shape[0] == n and inds.shape[1] == counts.max()
+        # properties on every row
+        sp = np.concatenate([pts, np.full((1, 3), 1e6, np.float32)], 0)
+        d = pts[:, None, :] - sp[inds]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]).astype(np.float32)
+        d2 = (d2 + d[..., 2] * d[..., 2]).astype(np.float32)
+        real = inds < n
+        assert np.array_equal(real.sum(1), counts)
+        assert np.all(real[:, :-1] >= real[:, 1:])                        # shadows only at the end
+        assert np.all(d2[real] < np.float32(radius) * np.float32(radius))  # strict radius, fp32 metric
+        d2s = np.where(real, d2, np.inf)
+        assert np.all(d2s[:, :-1] <= d2s[:, 1:])                          # sorted by distance
+        assert np.all(inds[:, 0] == np.arange(n))                         # the query itself comes first (d2 = 0)
+        # symmetry of the radius relation on a sample of pairs
+        qi = rng.integers(0, n, 2000)
+        for i in qi[:200]:
+            for j in inds[i, :counts[i]]:
+                assert i in inds[j, :counts[j]]
+        # exact agreement with the oracle on a subset of the rows
+        sel = np.sort(rng.choice(n, min(n, 3000), replace=False))
+        ref = geom.batch_neighbors(pts[sel], pts, np.array([len(sel)], np.int32), lens, radius)
+        w = ref.shape[1]
+        assert np.all(inds[sel, w:] == n) if inds.shape[1] > w else True
+        assert np.array_equal(inds[sel, :w], ref[:, :inds.shape[1]][:, :w])
+        # next level: subsampling is exact vs the oracle and idempotent in count
+        sub, sl = mvk.batch_grid_subsampling(pts, lens, sampleDl=dl, random_grid_orient=False)
+        rsub, rsl = geom.grid_subsample_batch(pts, lens, sampleDl=dl)
+        assert np.array_equal(sub, rsub) and np.array_equal(sl, rsl)
+        pts, radius, dl = sub, radius * 2, dl * 2
