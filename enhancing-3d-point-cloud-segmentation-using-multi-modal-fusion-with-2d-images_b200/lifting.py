@@ -150,6 +150,29 @@ class FeatureAggregation(nn.Module):
                               ptr(out), st))
         return out
 
+    def _needs_grad(self, *tensors):
+        return torch.is_grad_enabled() and (any(t is not None and t.requires_grad for t in tensors) or
+                                            any(p.requires_grad for p in self.parameters()))
+
+    def _run_autograd(self, X, np_, k):
+        """Differentiable pipeline (late fusion trains this module, architectures_sphere_late_fusion.py:
+        301-304): every layer is the fused Linear + batch norm + ReLU block of blocks.py
+        (tcgen05 contraction, fused statistics / activation kernels, hand-written backward)."""
+        from . import blocks as _b
+        cur = X
+        for layer in self.mlp:
+            bn = layer.bn
+            W = layer.conv.weight.reshape(layer.conv.out_channels, -1)
+            momentum = bn.momentum if bn.momentum is not None else 0.1
+            training = bn.training or not bn.track_running_stats
+            nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None
+            cur = _b._LinearBNAct.apply(cur, W, bn.weight, bn.bias, None, bn.running_mean, bn.running_var, True,
+                                        training, float(momentum), float(bn.eps), 0.0,
+                                        getattr(self, "contraction", None) or _b._kp.DEFAULT_CONTRACTION, nbt)
+        y = cur.view(np_, k, cur.shape[1])
+        out = y.sum(1) if self.reduction == 'sum' else y.max(1)[0]
+        return out.t()  # (cout, np)
+
     def forward(self, src_xyz, tgt_xyz, feature):
         """
         Args:
@@ -162,10 +185,14 @@ class FeatureAggregation(nn.Module):
         _lib.require_cuda()
         if not feature.is_cuda:
             raise RuntimeError("FeatureAggregation: tensors must live on a CUDA device (no CPU fallback)")
-        if torch.is_grad_enabled() and (feature.requires_grad or any(p.requires_grad for p in self.parameters())
-                                        ) and getattr(self, "_strict_grad", False):
-            raise NotImplementedError("FeatureAggregation backward is not implemented in the B200 path yet")
         b, c, np_, k = feature.shape
+        if self._needs_grad(feature, src_xyz, tgt_xyz):
+            diff = (src_xyz - tgt_xyz.unsqueeze(-1)).float()
+            dist = torch.sum(diff ** 2, dim=1, keepdim=True)
+            x = torch.cat([feature.float(), diff, dist], dim=1)  # (b, c+4, np, k)
+            X = x.permute(0, 2, 3, 1).reshape(b * np_ * k, c + 4).contiguous()
+            out = self._run_autograd(X, b * np_, k)  # (cout, b*np)
+            return out.reshape(-1, b, np_).permute(1, 0, 2).contiguous()
         with torch.no_grad(), torch.cuda.device(feature.device):
             diff = (src_xyz - tgt_xyz.unsqueeze(-1)).float()
             dist = torch.sum(diff ** 2, dim=1, keepdim=True)
@@ -189,6 +216,11 @@ class FeatureAggregation(nn.Module):
         c, npix = feature_2d.shape
         np_, k = knn_indices.shape
         dev = feature_2d.device
+        if feature_2d.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("forward_from_maps treats the 2D feature map as a constant (the 2D network is frozen in "
+                               "MV-KPConv, architectures_sphere.py:233-237); use group_points + forward() to "
+                               "back-propagate into it")
+        grad_path = self._needs_grad()
         with torch.no_grad(), torch.cuda.device(dev):
             f = feature_2d.detach().float()
             X = torch.empty((np_ * k, c + 4), dtype=torch.float32, device=dev)
@@ -196,7 +228,9 @@ class FeatureAggregation(nn.Module):
                                   f.stride(1), c, ptr(image_xyz.contiguous().float()),
                                   ptr(knn_indices.contiguous().long()), np_, k,
                                   ptr(tgt_points.contiguous().float()), ptr(X), c + 4, stream_ptr()))
-            return self._run(X, np_, k)
+            if not grad_path:
+                return self._run(X, np_, k)
+        return self._run_autograd(X, np_, k)
 
 
 # -------------------------------------------------------------------------------------------------

@@ -74,9 +74,13 @@ def test_feature_aggregation_vs_reference_golden(mvk, case):
     fa.eval()
     out = fa(src, tgt, feat)
     assert out.shape == c["out_eval"].shape
-    assert rel_err(out.cpu().numpy(), c["out_eval"]) < 1e-4
+    assert out.requires_grad  # parameters are trainable: the differentiable pipeline ran (like the reference)
+    assert rel_err(out.detach().cpu().numpy(), c["out_eval"]) < 1e-4
+    with torch.no_grad():      # inference pipeline (fused, no autograd bookkeeping)
+        assert rel_err(fa(src, tgt, feat).cpu().numpy(), c["out_eval"]) < 1e-4
     fa.train()
-    out = fa(src, tgt, feat)
+    with torch.no_grad():
+        out = fa(src, tgt, feat)
     assert rel_err(out.cpu().numpy(), c["out_train"]) < 1e-4
     # running statistics moved like nn.BatchNorm2d(momentum=0.1)
     for i in range(3):
@@ -100,3 +104,62 @@ def test_feature_aggregation_fused_gather_equals_group_points_path(mvk):
     # channels-last (pixel-major) feature maps are consumed through their strides
     fused2 = fa.forward_from_maps(feat2d.t().contiguous().t(), xyz, knn, tgt)
     assert torch.allclose(fused2, fused, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("contraction", ["fp32", "bf16x3"])
+def test_feature_aggregation_training_gradients_vs_oracle(mvk, contraction):
+    """Late fusion trains FeatureAggregation (architectures_sphere_late_fusion.py:301-304): forward in
+    train mode + gradients of every parameter and of the gathered features against autograd through
+    the torch restatement (which the reference goldens pin)."""
+    torch.manual_seed(4)
+    b, c, np_, k = 1, 64, 3000, 3
+    fa = mvk.FeatureAggregation(c).cuda().train()
+    fa.contraction = contraction
+    with torch.no_grad():
+        for l in fa.mlp:
+            l.bn.weight.uniform_(0.5, 1.5)
+            l.bn.bias.uniform_(-0.3, 0.3)
+    src = torch.randn(b, 3, np_, k)
+    tgt = torch.randn(b, 3, np_)
+    feat = torch.randn(b, c, np_, k)
+    go = torch.randn(b, 64, np_)
+    # oracle
+    fo = feat.clone().requires_grad_(True)
+    ws = [l.conv.weight.detach().cpu().clone().requires_grad_(True) for l in fa.mlp]
+    gs = [l.bn.weight.detach().cpu().clone().requires_grad_(True) for l in fa.mlp]
+    bs = [l.bn.bias.detach().cpu().clone().requires_grad_(True) for l in fa.mlp]
+    ref = modules.feature_aggregation_forward(src, tgt, fo, ws, gs, bs, None, None, True, "sum")
+    ref.backward(go)
+    # product
+    fg = feat.cuda().requires_grad_(True)
+    out = fa(src.cuda(), tgt.cuda(), fg)
+    out.backward(go.cuda())
+    tol = 2e-4
+    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < tol
+    # element-wise gradients: a ReLU whose pre-activation is within rounding of zero flips its mask, which
+    # changes isolated entries by O(1); compare the tensor as a whole and bound the number of outliers
+    # (measured: typical entries agree to 2e-5; a handful of flips per 1.7 M activations with the bf16x3
+    # contraction, none expected with the strict fp32 one)
+    ga, gb = fg.grad.cpu().numpy().astype(np.float64), fo.grad.numpy().astype(np.float64)
+    strict = contraction == "fp32"
+    assert np.linalg.norm(ga - gb) / np.linalg.norm(gb) < (2e-3 if strict else 3e-2)
+    assert (np.abs(ga - gb) > tol * np.abs(gb).max()).mean() < (1e-4 if strict else 2e-3)
+    # a flipped mask changes a weight gradient (a sum of ~N random-sign terms) by ~1/sqrt(N) of its size
+    ptol = 5 * tol if strict else 5e-2
+    for i, l in enumerate(fa.mlp):
+        assert rel_err(l.conv.weight.grad.cpu().numpy(), ws[i].grad.numpy()) < ptol, i
+        assert rel_err(l.bn.weight.grad.cpu().numpy(), gs[i].grad.numpy()) < ptol, i
+        assert rel_err(l.bn.bias.grad.cpu().numpy(), bs[i].grad.numpy()) < ptol, i
+        assert int(l.bn.num_batches_tracked) == 1
+    # the fused map entry point follows the same path when the module is being trained
+    torch.manual_seed(5)
+    npix = 3 * 19200
+    feat2d = torch.randn(c, npix, device="cuda")
+    xyz = torch.randn(npix, 3, device="cuda")
+    knn = torch.randint(0, npix, (np_, k), device="cuda")
+    tgtp = torch.randn(np_, 3, device="cuda")
+    fa.zero_grad()
+    o2 = fa.forward_from_maps(feat2d, xyz, knn, tgtp)
+    assert o2.requires_grad
+    o2.sum().backward()
+    assert fa.mlp[0].conv.weight.grad is not None and torch.isfinite(fa.mlp[0].conv.weight.grad).all()
