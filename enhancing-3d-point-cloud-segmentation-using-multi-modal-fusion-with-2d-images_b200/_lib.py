@@ -23,7 +23,7 @@ SIGNATURES = {
     "mvk_neighbors_count": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, vp, vp, vp]),
     "mvk_neighbors_fill": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, vp]),
     "mvk_neighbors_fill_i64": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, vp]),
-    "mvk_neighbors_query_capped": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, i32, vp, vp, vp]),
+    "mvk_neighbors_query_capped": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, i32, vp, vp, i32, vp]),
     "mvk_batch_neighbors_host": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, C.POINTER(vp), C.POINTER(i32)]),
     "mvk_subsample_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "mvk_grid_subsample": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp, vp]),

@@ -18,6 +18,7 @@ namespace {
 constexpr unsigned long long EMPTY_KEY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int CELL_BIAS = 1 << 17;
 constexpr int CELL_MAX = (1 << 18) - 2;
+constexpr int CAND_CAP = 256;  // flattened candidate list per query (falls back to the per-cell walk beyond)
 
 struct Grid {
     int* q_starts;              // [nb+1]
@@ -130,7 +131,7 @@ template <bool WRITE, typename OutT>
 __global__ void __launch_bounds__(256)
 k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, Grid g,
         int* __restrict__ counts, int* __restrict__ max_count, int list_cap, int width,
-        OutT* __restrict__ out, int ns) {
+        OutT* __restrict__ out, int ns, int cand_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
@@ -138,6 +139,8 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
     // hit list of this warp: one 64-bit key per hit = (d2 bits << 32) | support index.  d2 >= 0, so the
     // unsigned order of the keys IS the reference order (d2 ascending, index ascending on exact ties)
     unsigned long long* l_key = (unsigned long long*)smem_raw + (size_t)wib * list_cap;
+    // candidate slots of this warp (WRITE mode only): positions in g.sorted of every point of the 27 cells
+    int* own = (int*)((unsigned long long*)smem_raw + (size_t)wpb * list_cap) + (size_t)wib * CAND_CAP;
     const unsigned int mask = g.cap - 1;
     const int nq_valid = min(nq, g.q_starts[nb]);
     if (*g.err != 0) {  // a support fell outside the indexable cell range: report, do nothing
@@ -171,7 +174,45 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
                     }
                 }
             }
-            int maxc = ccnt;
+            // The 27 cells hold very different numbers of points (most are empty on surface data), so
+            // walking them lane-per-cell leaves most lanes idle: flatten the candidates first (prefix sum of
+            // the cell populations, candidate positions staged in shared memory), then test 32 candidates
+            // per trip.  The order of the hits does not matter: the rows are rank-sorted afterwards.
+            int incl = ccnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            bool flat = WRITE && total <= cand_cap;
+            if (flat) {
+                const int pre = incl - ccnt;
+                for (int t = 0; t < ccnt; t++) own[pre + t] = cstart + t;
+                __syncwarp();
+                for (int base = 0; base < total; base += 32) {
+                    const int cpos = base + lane;
+                    bool hit = false;
+                    float d2 = 0.f;
+                    int idx = 0;
+                    if (cpos < total) {
+                        const float4 c = g.sorted[own[cpos]];
+                        const float dx = __fsub_rn(qx, c.x), dy = __fsub_rn(qy, c.y), dz = __fsub_rn(qz, c.z);
+                        d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+                        idx = __float_as_int(c.w);
+                        hit = d2 < r2;
+                    }
+                    const unsigned int m = __ballot_sync(0xffffffffu, hit);
+                    if (hit) {
+                        const int pos = nfound + __popc(m & ((1u << lane) - 1));
+                        if (pos < list_cap)
+                            l_key[pos] = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)idx;
+                    }
+                    nfound += __popc(m);
+                }
+                __syncwarp();
+            }
+            int maxc = flat ? 0 : ccnt;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, o));
             for (int it = 0; it < maxc; it++) {
@@ -225,6 +266,11 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
     }
 }
 
+int flat_cap() {  // development switch: MVK_NB_FLAT=0 restores the lane-per-cell candidate walk
+    static const char* e = getenv("MVK_NB_FLAT");
+    return (e && e[0] == '0') ? -1 : CAND_CAP;
+}
+
 int build(const float* s, int ns, const int* ql, const int* sl, int nb, float radius, Grid& g,
           cudaStream_t st) {
     double inv_cell = 1.0 / ((double)radius * 1.00001);
@@ -255,7 +301,7 @@ int fill(const float* q, int nq, const float* s, int ns, int nb, float radius, v
     Arena a(ws, ws_bytes);
     Grid g = carve(a, nq, ns, nb);
     int list_cap = max_count < 32 ? 32 : (max_count + 31) / 32 * 32;
-    size_t per_warp = (size_t)list_cap * 8;
+    size_t per_warp = (size_t)list_cap * 8 + CAND_CAP * 4;
     if (per_warp > 200 * 1024) return MVK_ERR_RANGE;
     int wpb = (int)((64 * 1024) / per_warp);
     wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
@@ -268,7 +314,7 @@ int fill(const float* q, int nq, const float* s, int ns, int nb, float radius, v
     float r2 = radius * radius;
     double inv_cell = 1.0 / ((double)radius * 1.00001);
     kern<<<blocks, wpb * 32, smem, st>>>(q, nq, nb, r2, inv_cell, g, nullptr, nullptr, list_cap,
-                                         width, out, ns);
+                                         width, out, ns, flat_cap());
     MVK_LAUNCHED("k_query<fill>");
     return MVK_OK;
 }
@@ -276,19 +322,26 @@ int fill(const float* q, int nq, const float* s, int ns, int nb, float radius, v
 template <typename OutT>
 int query_capped(const float* q, int nq, const float* s, int ns, const int* ql, const int* sl, int nb, float radius,
                  void* ws, size_t ws_bytes, int width, int list_cap, OutT* out, int* counts, int* max_count,
-                 cudaStream_t st) {
+                 int reuse_grid, cudaStream_t st) {
     if (nq < 0 || ns < 0 || nb < 1 || nb > 1023 || !(radius > 0.f) || width < 1 || list_cap < width || !out ||
         !max_count)
         return MVK_ERR_INVALID_ARG;
     if (ws_bytes < mvk_neighbors_workspace_bytes(nq, ns, nb) || !ws) return MVK_ERR_WORKSPACE;
     Arena a(ws, ws_bytes);
     Grid g = carve(a, nq, ns, nb);
-    int rc = build(s, ns, ql, sl, nb, radius, g, st);
-    if (rc) return rc;
+    if (reuse_grid) {
+        // the workspace still holds the cell grid of these supports at this radius (previous call): only
+        // the batch offsets of the new queries are needed
+        k_starts<<<1, 32, 0, st>>>(ql, sl, nb, g.q_starts, g.s_starts);
+        MVK_LAUNCHED("k_starts");
+    } else {
+        int rc = build(s, ns, ql, sl, nb, radius, g, st);
+        if (rc) return rc;
+    }
     MVK_CUDA(cudaMemsetAsync(max_count, 0, sizeof(int), st));
     if (nq == 0) return MVK_OK;
     list_cap = (list_cap + 31) / 32 * 32;
-    size_t per_warp = (size_t)list_cap * 8;
+    size_t per_warp = (size_t)list_cap * 8 + CAND_CAP * 4;
     if (per_warp > 200 * 1024) return MVK_ERR_RANGE;
     int wpb = (int)((64 * 1024) / per_warp);
     wpb = wpb < 1 ? 1 : (wpb > 8 ? 8 : wpb);
@@ -300,7 +353,8 @@ int query_capped(const float* q, int nq, const float* s, int ns, const int* ql, 
     if (blocks > max_blocks) blocks = max_blocks;
     float r2 = radius * radius;
     double inv_cell = 1.0 / ((double)radius * 1.00001);
-    kern<<<blocks, wpb * 32, smem, st>>>(q, nq, nb, r2, inv_cell, g, counts, max_count, list_cap, width, out, ns);
+    kern<<<blocks, wpb * 32, smem, st>>>(q, nq, nb, r2, inv_cell, g, counts, max_count, list_cap, width, out, ns,
+                                         flat_cap());
     MVK_LAUNCHED("k_query<capped>");
     return MVK_OK;
 }
@@ -338,7 +392,7 @@ int mvk_neighbors_count(const float* queries, int nq, const float* supports, int
     float r2 = radius * radius;  // fp32 product like neighbors.cpp:226
     double inv_cell = 1.0 / ((double)radius * 1.00001);
     k_query<false, int><<<blocks, wpb * 32, 0, st>>>(queries, nq, nb, r2, inv_cell, g, counts,
-                                                     max_count, 0, 0, nullptr, ns);
+                                                     max_count, 0, 0, nullptr, ns, 0);
     MVK_LAUNCHED("k_query<count>");
     return MVK_OK;
 }
@@ -365,12 +419,12 @@ int mvk_neighbors_fill_i64(const float* queries, int nq, const float* supports, 
 int mvk_neighbors_query_capped(const float* queries, int nq, const float* supports, int ns, const int* q_lengths,
                                const int* s_lengths, int nb, float radius, void* ws, size_t ws_bytes, int width,
                                int list_cap, void* out, int out_is_i64, int* counts, int* max_count,
-                               mvk_stream_t stream) {
+                               int reuse_grid, mvk_stream_t stream) {
     if (out_is_i64)
         return query_capped<long long>(queries, nq, supports, ns, q_lengths, s_lengths, nb, radius, ws, ws_bytes, width,
-                                       list_cap, (long long*)out, counts, max_count, (cudaStream_t)stream);
+                                       list_cap, (long long*)out, counts, max_count, reuse_grid, (cudaStream_t)stream);
     return query_capped<int>(queries, nq, supports, ns, q_lengths, s_lengths, nb, radius, ws, ws_bytes, width, list_cap,
-                             (int*)out, counts, max_count, (cudaStream_t)stream);
+                             (int*)out, counts, max_count, reuse_grid, (cudaStream_t)stream);
 }
 
 int mvk_batch_neighbors_host(const float* qh, int nq, const float* sh, int ns, const int* qlh,

@@ -16,15 +16,19 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 _WS = {}
+_GRID = {}  # device -> signature of the cell grid currently sitting in the neighbour workspace
 
 
-def _workspace(nbytes, device):
-    """Grow-only scratch buffer per device (the C ABI never allocates)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+def _workspace(nbytes, device, kind="subsample"):
+    """Grow-only scratch buffer per device and kind (the C ABI never allocates).  Radius search and
+    subsampling use separate buffers so that a cell grid survives the subsampling call in between."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), kind)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
         _WS[key] = buf
+        if kind == "neighbors":
+            _GRID.pop(key[0], None)
     return buf
 
 
@@ -96,7 +100,17 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
     nq, ns, nb = q.shape[0], s.shape[0], qb.numel()
     with _lib.on_device(dev):
         wsb = L.mvk_neighbors_workspace_bytes(nq, ns, nb)
-        ws = _workspace(wsb, dev)
+        ws = _workspace(wsb, dev, "neighbors")
+        dkey = dev.index if dev.index is not None else torch.cuda.current_device()
+        # Is the grid in `ws` the one of THIS support tensor (same object, unmodified), batch split, radius?
+        # The cache keeps the tensors alive, so a match cannot be a recycled address with other contents.
+        sig = None
+        if isinstance(supports, torch.Tensor) and isinstance(s_batches, torch.Tensor):
+            sig = (s, s._version, sb, sb.data_ptr(), sb._version, ns, nb, float(np.float32(radius)),
+                   torch._C._cuda_getCurrentRawStream(dkey))
+        old = _GRID.pop(dkey, None)  # whatever runs below rebuilds or invalidates it
+        reuse = 1 if (sig is not None and old is not None and old[0] is sig[0] and old[1] == sig[1] and
+                      old[3:] == sig[3:]) else 0
         counts = torch.empty(max(nq, 1), dtype=torch.int32, device=dev)
         hmax = torch.zeros(1, dtype=torch.int32, device=dev)
         if max_neighbors is not None and nq > 0:
@@ -106,7 +120,9 @@ def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbo
             out = torch.empty((nq, width), dtype=out_dtype, device=dev)
             check(L.mvk_neighbors_query_capped(ptr(q), nq, ptr(s), ns, ptr(qb), ptr(sb), nb, float(radius), ptr(ws),
                                                ws.numel(), width, cap, ptr(out), 1 if out_dtype == torch.int64 else 0,
-                                               ptr(counts), ptr(hmax), stream_ptr()))
+                                               ptr(counts), ptr(hmax), reuse, stream_ptr()))
+            if sig is not None:
+                _GRID[dkey] = sig  # the grid of (supports, radius) now sits in the workspace
             if deferred is not None and not as_np and not return_counts:
                 args = (queries, supports, q_batches, s_batches, radius, max_neighbors, out_dtype)
                 deferred.append(SimpleNamespace(hmax=hmax, width=width, cap=cap, out=out, args=args))

@@ -78,11 +78,13 @@ int mvk_neighbors_fill_i64(const float* queries, int nq, const float* supports, 
  * *max_count (device int) receives the true maximum hit count: if it exceeds list_cap the rows of
  * such queries may be wrong and the caller must fall back to the two-phase protocol; if it is
  * smaller than width the caller crops the columns (reference width = min(max_count, limit)).
- * counts may be NULL. */
+ * counts may be NULL.  reuse_grid != 0 skips the grid build: `ws` must still hold the grid that the
+ * previous call built for the SAME supports, s_lengths and radius (the pyramid queries one support
+ * cloud three times per level: up-sampling of the finer level, convolution, pooling). */
 int mvk_neighbors_query_capped(const float* queries, int nq, const float* supports, int ns, const int* q_lengths,
                                const int* s_lengths, int nb, float radius, void* ws, size_t ws_bytes, int width,
                                int list_cap, void* out, int out_is_i64, int* counts, int* max_count,
-                               mvk_stream_t stream);
+                               int reuse_grid, mvk_stream_t stream);
 /* Host-buffer convenience entry point == the reference call: all pointers are HOST pointers,
  * *out_host is malloc'ed [nq, *width] int32 (free with mvk_free_host).  Copies H2D, runs both
  * phases on the default stream, copies D2H.  Returns MVK_ERR_EMPTY when nq * max_count == 0

@@ -126,7 +126,8 @@ def test_gemm_fused_column_statistics(mvk):
         lo = lambda t: (t - t.bfloat16().float()).bfloat16()
         D = torch.zeros(M, N, device="cuda")
         stats = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
-        check(L.mvk_gemm_bf16x3_stats(ptr(hi(A)), ptr(lo(A)), 0, K, ptr(hi(B)), ptr(lo(B)), 0, K, M, N, K, ptr(D), N, N, 3, 0,
+        a_hi, a_lo, b_hi, b_lo = hi(A), lo(A), hi(B), lo(B)  # keep the operands alive across the call
+        check(L.mvk_gemm_bf16x3_stats(ptr(a_hi), ptr(a_lo), 0, K, ptr(b_hi), ptr(b_lo), 0, K, M, N, K, ptr(D), N, N, 3, 0,
                                       ptr(stats), stream_ptr()))
         ref = A.double() @ B.double().t()
         assert rel_err(D, ref) < 2e-5
