@@ -224,10 +224,12 @@ class FeatureAggregation(nn.Module):
         with torch.no_grad(), torch.cuda.device(dev):
             f = feature_2d.detach().float()
             X = torch.empty((np_ * k, c + 4), dtype=torch.float32, device=dev)
-            check(L.mvk_fa_gather(ptr(f) if f.is_contiguous() else _lib.C.c_void_p(f.data_ptr()), f.stride(0),
-                                  f.stride(1), c, ptr(image_xyz.contiguous().float()),
-                                  ptr(knn_indices.contiguous().long()), np_, k,
-                                  ptr(tgt_points.contiguous().float()), ptr(X), c + 4, stream_ptr()))
+            # converted copies must outlive the call: keep them in locals (a temporary freed between two
+            # ptr() evaluations could hand its memory to the next temporary)
+            xyz_c, knn_c, tgt_c = image_xyz.contiguous().float(), knn_indices.contiguous().long(), \
+                tgt_points.contiguous().float()
+            check(L.mvk_fa_gather(f.data_ptr(), f.stride(0), f.stride(1), c, ptr(xyz_c), ptr(knn_c), np_, k, ptr(tgt_c),
+                                  ptr(X), c + 4, stream_ptr()))
             if not grad_path:
                 return self._run(X, np_, k)
         return self._run_autograd(X, np_, k)
