@@ -150,12 +150,12 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
         if (cok) {
             const float* yc = y + (size_t)(c0 + tx) * VEC;
             int r = r0 + ty;
-            for (; r + 3 * m.rpi < r1; r += 4 * m.rpi) {  // four independent loads in flight
-                float v[4][VEC];
+            for (; r + 7 * m.rpi < r1; r += 8 * m.rpi) {  // eight independent loads in flight
+                float v[8][VEC];
 #pragma unroll
-                for (int u = 0; u < 4; u++) loadv<VEC>(yc + (size_t)(r + u * m.rpi) * ld, v[u]);
+                for (int u = 0; u < 8; u++) loadv<VEC>(yc + (size_t)(r + u * m.rpi) * ld, v[u]);
 #pragma unroll
-                for (int u = 0; u < 4; u++)
+                for (int u = 0; u < 8; u++)
 #pragma unroll
                     for (int e = 0; e < VEC; e++) {
                         part[0][e] += v[u][e];
@@ -383,7 +383,7 @@ inline int vec_for(int cols, int a, int b, int c, int d) {
 inline int slab_rows(int rows, int cols, int vec, dim3* grid) {
     Map2D m = make_map2d(cols, vec);
     const int ncg = (m.cv + m.cpb - 1) / m.cpb;  // column groups (blockIdx.y)
-    int target = num_sms() * 2 / ncg;            // same-address fp64 atomics serialise in L2: few, fat CTAs
+    int target = num_sms() * 4 / ncg;            // same-address fp64 atomics serialise in L2: few, fat CTAs
     if (target < 1) target = 1;
     int rpc = (rows + target - 1) / target;
     rpc = (rpc + m.rpi - 1) / m.rpi * m.rpi;
