@@ -18,6 +18,10 @@ SHAPES = [  # M, N, K, a_mn, b_mn, split, tag
     (267103, 384, 128, 0, 1, 0, "unary dx 128->384"), (128, 384, 267103, 1, 1, 98, "unary dW 384->128"),
     (267103, 128, 128, 0, 0, 0, "unary 128->128 L0"), (128, 128, 267103, 1, 1, 296, "unary dW 128"),
     (51312, 256, 768, 0, 0, 0, "unary 768->256 L1"), (51312, 768, 256, 0, 1, 0, "unary dx L1"),
+    # tensor-bound shapes (whole-scene sweeps / wide layers): where the tensor-pipe fraction is read
+    (65536, 512, 7680, 0, 1, 0, "tensor fwd 512->512 64k pts"), (65536, 7680, 512, 0, 0, 0, "tensor dA 512 64k pts"),
+    (7680, 512, 65536, 1, 1, 0, "tensor dW 512 64k pts"), (262144, 256, 3840, 0, 1, 0, "tensor fwd 256->256 262k pts"),
+    (8192, 8192, 8192, 0, 0, 0, "tensor square 8k"),
 ]
 
 def main():
