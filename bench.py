@@ -168,16 +168,15 @@ def run_b200(args):
     host_enqueue_ms = [0.0]
     per_rank = []
 
-    def step(from_host):
-        if from_host:
-            p = pts_p.to(dev, non_blocking=True)
-            f = feats_p.to(dev, non_blocking=True)
-            y = labels_p.to(dev, non_blocking=True)
-            ln = lens_p.to(dev, non_blocking=True)
-        else:
-            p, f, y, ln = pts_d, feats_d, labels_d, lens_d
+    def load_inputs(from_host):
+        """(points, lengths, (features, labels)) of one batch; from_host: H2D copies from pinned memory."""
         np.random.seed(1)  # batch_grid_subsampling draws its grid orientations from np.random
-        pyr = pyramid.build_pyramid(p, ln, cfg)
+        if from_host:
+            return (pts_p.to(dev, non_blocking=True), lens_p.to(dev, non_blocking=True),
+                    (feats_p.to(dev, non_blocking=True), labels_p.to(dev, non_blocking=True)))
+        return pts_d, lens_d, (feats_d, labels_d)
+
+    def train(pyr, f, y):
         batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools,
                                 upsamples=pyr.upsamples, lengths=pyr.lengths, features=f, labels=y)
         queries_per_step[0] = sum(t.shape[0] for t in pyr.neighbors + pyr.pools + pyr.upsamples)
@@ -189,11 +188,51 @@ def run_b200(args):
             allreduce_grads()
         torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)  # utils/trainer.py:191-193
         opt.step()
+        return loss
+
+    def step(from_host):
+        """One un-pipelined step (profiling passes and --no-prefetch): pyramid, then training, one stream."""
+        p, ln, (f, y) = load_inputs(from_host)
+        loss = train(pyramid.build_pyramid(p, ln, cfg), f, y)
         return loss.item() if from_host else loss
 
+    prefetch = None if args.no_prefetch else pyramid.PyramidPrefetcher(cfg, dev)
+    loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()  # read-back slots of the e2e arm
+
+    def run_steps(from_host, steps):
+        """`steps` steps; with the prefetcher the pyramid of batch i+1 is enqueued on the side stream
+        after batch i's training launches, so K steps contain K pyramid builds and K training passes.
+        from_host: every step's loss is read back (one step late, so the read never drains the queue)."""
+        if prefetch is None:
+            last = None
+            for _ in range(steps):
+                last = step(from_host)
+            return last
+        last, prev_ev = None, None
+        for i in range(steps):
+            pyr, (f, y) = prefetch.take()
+            loss = train(pyr, f, y)
+            if from_host:
+                slot = loss_pin[i % 2:i % 2 + 1]
+                slot.copy_(loss.detach().reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if prev_ev is not None:
+                    prev_ev[0].synchronize()
+                    last = float(prev_ev[1])
+                prev_ev = (ev, slot)
+            prefetch.submit(lambda: load_inputs(from_host))
+        if from_host:
+            prev_ev[0].synchronize()
+            return float(prev_ev[1])
+        return loss
+
     def timed(from_host, steps, warmup, sample_clocks=False):
-        for _ in range(warmup):
-            step(from_host)
+        if prefetch is not None:
+            if prefetch._pending is not None:
+                prefetch.take()  # left over from the previous timed region (other input source)
+            prefetch.submit(lambda: load_inputs(from_host))
+        run_steps(from_host, warmup)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -202,10 +241,10 @@ def run_b200(args):
         l0 = L.mvk_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        last = None
         t_host0 = time.perf_counter()
-        for _ in range(steps):
-            last = step(from_host)
+        last = run_steps(from_host, steps)
+        if prefetch is not None:  # the pyramid enqueued by the last step belongs to the timed region
+            torch.cuda.current_stream().wait_stream(prefetch.stream)
         e1.record()
         host_enqueue_ms[0] = 1e3 * (time.perf_counter() - t_host0) / steps  # host time to ENQUEUE a step
         torch.cuda.synchronize()
@@ -351,6 +390,9 @@ def run_b200(args):
                        "spheres_per_gpu": SPHERES_PER_GPU, "points_per_gpu": n_pts, "in_radius": IN_RADIUS,
                        "first_subsampling_dl": FIRST_DL, "K": 15, "neighborhood_limits": cfg.neighborhood_limits,
                        "parallelism": (f"sphere-sharded x{world}, gradient all-reduce (NCCL, {args.allreduce})" if world > 1 else "single GPU"),
+                       "pipeline": ("one stream: pyramid, forward, backward, SGD in sequence" if args.no_prefetch else
+                                    "pyramid of batch i+1 built on a side stream while batch i trains "
+                                    "(K timed steps = K pyramids + K training passes)"),
                        "l2": "per-step working set (saved [N,15*Cin] operands, >1 GB) far exceeds the 126 MB L2; no flush"},
             "e2e": {"value": round(total_pts * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d),
@@ -474,6 +516,9 @@ def main():
                     help="N > 1: one coalesced NCCL all-reduce of the gradients after backward, or torch DDP buckets")
     ap.add_argument("--detail", type=int, default=0, help="add the N most expensive (entry point, shape) rows")
     ap.add_argument("--quick", action="store_true", help="device-resident timed region only (for ncu runs)")
+    ap.add_argument("--no-prefetch", action="store_true",
+                    help="build each batch's pyramid on the training stream right before its forward pass "
+                         "(default: pyramid of batch i+1 on a side stream while batch i trains)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3  # timing rule: W >= 3

@@ -4,7 +4,10 @@
 // The Linear of the unary block runs on the tcgen05 contraction (gemm_tc.cu); everything here is
 // HBM-bound streaming over [rows, cols] fp32 matrices:
 //   thread (tx, ty): tx = column vector (VEC floats), ty = row inside the CTA's row slab;
-//   column sums are reduced through shared memory and leave as one fp64 atomic per column and CTA.
+//   column sums are reduced through shared memory, then across the CTAs of a thread-block cluster
+//   through distributed shared memory, and leave as one fp64 atomic per column and CLUSTER
+//   (ATOMG.F64 is slow on sm_100: ~75 k of them cost 8 us, see scripts/stats_bench.py).
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -12,7 +15,10 @@
 namespace mvk {
 namespace {
 
+namespace cg = cooperative_groups;
+
 constexpr int TB = 256;
+constexpr int CLUSTER = 8;  // CTAs (row slabs) per cluster in the column reductions
 
 struct Map2D {
     int cv;    // vector columns per row (cols / VEC)
@@ -75,27 +81,35 @@ __device__ __forceinline__ void store_hilo<4>(__nv_bfloat16* hi, __nv_bfloat16* 
     *(uint2*)lo = pl;
 }
 
-// Reduces NV per-thread partial column vectors over the CTA's `rpi` thread rows and adds them
-// to out[q * cols + column] (fp64 atomics).  red: shared [NV][TB * VEC].
+// Reduces NV per-thread partial column vectors over the CTA's `rpi` thread rows, then over the CTAs of
+// the cluster (which all share blockIdx.y), and adds them to out[q * cols + column] (one fp64 atomic per
+// column and cluster, issued by cluster rank 0).  red: shared [NV][TB * VEC]; csum: shared [NV * 32 * VEC].
 template <int VEC, int NV>
-__device__ __forceinline__ void reduce_columns(float (&part)[NV][VEC], float* red, const Map2D& m, int tx, int ty,
-                                               bool active, int c0, int cols, double* out) {
+__device__ __forceinline__ void reduce_columns(float (&part)[NV][VEC], float* red, float* csum, const Map2D& m, int tx,
+                                               int ty, bool active, int c0, int cols, double* out) {
+    cg::cluster_group cluster = cg::this_cluster();
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < NV; q++)
 #pragma unroll
-        for (int e = 0; e < VEC; e++) red[(q * TB + threadIdx.x) * VEC + e] = active ? part[q][e] : 0.f;
+        for (int e = 0; e < VEC; e++) red[(q * TB + ty * m.cpb + tx) * VEC + e] = active ? part[q][e] : 0.f;
     __syncthreads();
-    if (active && ty == 0) {
-#pragma unroll
-        for (int q = 0; q < NV; q++)
-#pragma unroll
-            for (int e = 0; e < VEC; e++) {
-                float s = 0.f;
-                for (int r = 0; r < m.rpi; r++) s += red[(q * TB + r * m.cpb + tx) * VEC + e];
-                atomicAdd(&out[(size_t)q * cols + (size_t)(c0 + tx) * VEC + e], (double)s);
-            }
+    // value v = (q, tx, e): every thread sums one value over the rpi thread rows (conflict-free)
+    const int per_q = m.cpb * VEC, nval = NV * per_q;
+    const int v = threadIdx.x, q = v / per_q, rem = v % per_q;
+    if (v < nval) {
+        float s0 = 0.f;
+        for (int r = 0; r < m.rpi; r++) s0 += red[q * TB * VEC + r * per_q + rem];
+        csum[v] = s0;
     }
+    cluster.sync();
+    if (cluster.block_rank() == 0 && v < nval && c0 + rem / VEC < m.cv) {
+        double tot = 0.0;
+        const unsigned int nb = cluster.num_blocks();
+        for (unsigned int b = 0; b < nb; b++) tot += (double)cluster.map_shared_rank(csum, b)[v];
+        atomicAdd(&out[(size_t)q * cols + (size_t)c0 * VEC + rem], tot);
+    }
+    cluster.sync();  // csum stays alive until rank 0 has read it
 }
 
 struct BnFin {
@@ -112,21 +126,35 @@ struct BnFin {
     long long* num_batches_tracked;  // optional: += 1 (torch.nn.BatchNorm1d bookkeeping)
 };
 
-__device__ __forceinline__ void bn_finalize_column(const double s0, const double s1, int rows, int c, const BnFin& f) {
-    const double mu = s0 / rows;
-    double var = s1 / rows - mu * mu;
+// Per-column batch-norm bookkeeping with the inputs already in registers (the caller issues the loads of
+// several columns before the first use: the last CTA's chain of L2 round trips is the tail of the kernel).
+struct BnColIn {
+    double s0, s1;
+    float rm, rv, g, b;
+};
+__device__ __forceinline__ BnColIn bn_load_column(const double* stats, int cols, int c, const BnFin& f) {
+    BnColIn in;
+    in.s0 = __ldcg(stats + c);
+    in.s1 = __ldcg(stats + cols + c);
+    in.rm = f.running_mean ? f.running_mean[c] : 0.f;
+    in.rv = f.running_mean ? f.running_var[c] : 0.f;
+    in.g = f.gamma ? f.gamma[c] : 1.f;
+    in.b = f.beta ? f.beta[c] : 0.f;
+    return in;
+}
+__device__ __forceinline__ void bn_finalize_column(const BnColIn& in, int rows, int c, const BnFin& f) {
+    const double mu = in.s0 / rows;
+    double var = in.s1 / rows - mu * mu;
     if (var < 0.0) var = 0.0;
     const float mean = (float)mu;
     const float invstd = (float)(1.0 / sqrt(var + (double)f.eps));
     if (f.running_mean) {
         const double unbiased = rows > 1 ? var * ((double)rows / (double)(rows - 1)) : var;
-        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
-        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+        f.running_mean[c] = (1.f - f.momentum) * in.rm + f.momentum * mean;
+        f.running_var[c] = (1.f - f.momentum) * in.rv + f.momentum * (float)unbiased;
     }
-    const float g = f.gamma ? f.gamma[c] : 1.f;
-    const float b = f.beta ? f.beta[c] : 0.f;
-    f.scale[c] = g * invstd;
-    f.shift[c] = b - mean * g * invstd;
+    f.scale[c] = in.g * invstd;
+    f.shift[c] = in.b - mean * in.g * invstd;
     if (f.mean_out) f.mean_out[c] = mean;
     if (f.invstd_out) f.invstd_out[c] = invstd;
 }
@@ -137,6 +165,7 @@ __global__ void __launch_bounds__(TB)
 col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double* __restrict__ stats, int rows_per_cta,
                  BnFin fin) {
     __shared__ float red[2 * TB * VEC];
+    __shared__ float csum[2 * 32 * VEC];
     __shared__ unsigned int s_last;
     const Map2D m = make_map2d(cols, VEC);
     const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
@@ -172,7 +201,7 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
                 }
             }
         }
-        reduce_columns<VEC, 2>(part, red, m, tx, ty, cok, c0, cols, stats);
+        reduce_columns<VEC, 2>(part, red, csum, m, tx, ty, cok, c0, cols, stats);
     }
     if (fin.ticket) {
         // the CTA that retires last turns the column sums into scale / shift / running statistics
@@ -183,9 +212,14 @@ col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double
         if (s_last) {
             __threadfence();
             if (threadIdx.x == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
-            for (int c = threadIdx.x; c < cols; c += TB) {
-                const double s0 = __ldcg(stats + c), s1 = __ldcg(stats + cols + c);
-                bn_finalize_column(s0, s1, rows, c, fin);
+            for (int cb = threadIdx.x; cb < cols; cb += 4 * TB) {
+                BnColIn in[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (cb + u * TB < cols) in[u] = bn_load_column(stats, cols, cb + u * TB, fin);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (cb + u * TB < cols) bn_finalize_column(in[u], rows, cb + u * TB, fin);
             }
         }
     }
@@ -272,6 +306,7 @@ act_bwd_reduce_kernel(const float* __restrict__ dz, int lddz, const float* __res
                       const float* __restrict__ residual, int ldr, const float* __restrict__ mean,
                       const float* __restrict__ invstd, float slope, double* __restrict__ sums, int rows_per_cta) {
     __shared__ float red[2 * TB * VEC];
+    __shared__ float csum[2 * 32 * VEC];
     const Map2D m = make_map2d(cols, VEC);
     const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
     const bool active = ty < m.rpi;
@@ -315,7 +350,7 @@ act_bwd_reduce_kernel(const float* __restrict__ dz, int lddz, const float* __res
                     }
             }
         }
-        reduce_columns<VEC, 2>(part, red, m, tx, ty, cok, c0, cols, sums);
+        reduce_columns<VEC, 2>(part, red, csum, m, tx, ty, cok, c0, cols, sums);
     }
 }
 
@@ -380,16 +415,36 @@ __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int cols,
 inline int vec_for(int cols, int a, int b, int c, int d) {
     return (cols % 4 == 0 && a % 4 == 0 && b % 4 == 0 && c % 4 == 0 && d % 4 == 0) ? 4 : 1;
 }
-inline int slab_rows(int rows, int cols, int vec, dim3* grid) {
+inline int slab_rows(int rows, int cols, int vec, dim3* grid, int* cluster) {
     Map2D m = make_map2d(cols, vec);
     const int ncg = (m.cv + m.cpb - 1) / m.cpb;  // column groups (blockIdx.y)
-    int target = num_sms() * 4 / ncg;            // same-address fp64 atomics serialise in L2: few, fat CTAs
+    int target = num_sms() * 2 / ncg;            // ~2 fat CTAs per SM
     if (target < 1) target = 1;
     int rpc = (rows + target - 1) / target;
     rpc = (rpc + m.rpi - 1) / m.rpi * m.rpi;
     if (rpc < m.rpi * 4) rpc = m.rpi * 4;
-    *grid = dim3((rows + rpc - 1) / rpc, ncg, 1);
+    int gx = (rows + rpc - 1) / rpc;
+    *cluster = gx >= CLUSTER ? CLUSTER : 1;
+    gx = (gx + *cluster - 1) / *cluster * *cluster;  // CTAs past the last slab see an empty row range
+    *grid = dim3(gx, ncg, 1);
     return rpc;
+}
+// Launch with a (cluster, 1, 1) thread-block cluster.
+template <typename... KArgs, typename... Args>
+inline void launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cluster, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TB, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 inline int ew_grid(size_t total) {
     size_t b = (total + TB - 1) / TB;
@@ -409,10 +464,11 @@ int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk
     if (rows == 0) return MVK_OK;
     const int vec = vec_for(cols, ld, 4, 4, 4);
     dim3 grid;
-    const int rpc = slab_rows(rows, cols, vec, &grid);
+    int cl;
+    const int rpc = slab_rows(rows, cols, vec, &grid, &cl);
     BnFin fin = {};
-    if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
-    else col_stats_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
+    if (vec == 4) launch_clustered(col_stats_kernel<4>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
+    else launch_clustered(col_stats_kernel<1>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
     MVK_LAUNCHED("col_stats");
     return MVK_OK;
 }
@@ -424,11 +480,12 @@ int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats
     if (!y || !stats || rows < 1 || cols < 1 || ld < cols || !scale || !shift) return MVK_ERR_INVALID_ARG;
     const int vec = vec_for(cols, ld, 4, 4, 4);
     dim3 grid;
-    const int rpc = slab_rows(rows, cols, vec, &grid);
+    int cl;
+    const int rpc = slab_rows(rows, cols, vec, &grid, &cl);
     BnFin fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean_out, invstd_out,
                  (unsigned int*)(stats + 2 * (size_t)cols), num_batches_tracked};
-    if (vec == 4) col_stats_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
-    else col_stats_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, stats, rpc, fin);
+    if (vec == 4) launch_clustered(col_stats_kernel<4>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
+    else launch_clustered(col_stats_kernel<1>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
     MVK_LAUNCHED("col_stats+finalize");
     return MVK_OK;
 }
@@ -474,13 +531,14 @@ int mvk_act_bwd_reduce(const float* dz, int lddz, const float* y, int rows, int 
     if (rows == 0) return MVK_OK;
     const int vec = vec_for(cols, ld, lddz, residual ? ldr : 4, 4);
     dim3 grid;
-    const int rpc = slab_rows(rows, cols, vec, &grid);
+    int cl;
+    const int rpc = slab_rows(rows, cols, vec, &grid, &cl);
     if (vec == 4)
-        act_bwd_reduce_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(dz, lddz, y, rows, cols, ld, scale, shift,
-                                                                       residual, ldr, mean, invstd, slope, sums, rpc);
+        launch_clustered(act_bwd_reduce_kernel<4>, grid, cl, (cudaStream_t)stream, dz, lddz, y, rows, cols, ld, scale,
+                         shift, residual, ldr, mean, invstd, slope, sums, rpc);
     else
-        act_bwd_reduce_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(dz, lddz, y, rows, cols, ld, scale, shift,
-                                                                       residual, ldr, mean, invstd, slope, sums, rpc);
+        launch_clustered(act_bwd_reduce_kernel<1>, grid, cl, (cudaStream_t)stream, dz, lddz, y, rows, cols, ld, scale,
+                         shift, residual, ldr, mean, invstd, slope, sums, rpc);
     MVK_LAUNCHED("act_bwd_reduce");
     return MVK_OK;
 }

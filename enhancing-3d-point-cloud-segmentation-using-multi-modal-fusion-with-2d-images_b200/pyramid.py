@@ -140,3 +140,73 @@ def calibrate_neighborhood_limits(stacked_points, stack_lengths, config, ops=Non
         counts = (t < ns).sum(1).float()
         limits.append(max(1, int(torch.quantile(counts.cpu(), keep).item())))
     return limits
+
+
+class PyramidPrefetcher:
+    """Builds the pyramid of the NEXT batch on a side CUDA stream while the current batch trains.
+
+    The reference overlaps the same two things with processes: ``segmentation_inputs`` runs inside the
+    DataLoader workers (``num_workers = config.input_threads``, training scripts e.g.
+    train_ScanNet_baseline.py:303-315) while the trainer consumes the previous batch
+    (utils/trainer.py:160-200).  Here one host thread does both: the pyramid's launches and its few
+    size read-backs go to ``self.stream``, so a read-back waits for the side stream only and never
+    drains the backlog of forward/backward kernels queued on the training stream.
+
+        pf = PyramidPrefetcher(cfg, device)
+        pf.submit(lambda: (points, lengths, extras))    # batch 0
+        for ...:
+            pyr, extras = pf.take()                     # batch i, ready on the current stream
+            ... enqueue forward / backward / optimiser of batch i ...
+            pf.submit(loader_for_batch_i_plus_1)        # its launches overlap batch i's kernels
+
+    ``make_inputs`` runs with the side stream current, so host->device copies issued inside it
+    (``.to(device, non_blocking=True)`` from pinned memory) are part of the pipeline too.  Every tensor
+    handed out by ``take`` is marked with ``record_stream`` so that the caching allocator does not
+    recycle it for the next pyramid while training kernels still read it.
+    """
+
+    def __init__(self, config, device, index_dtype=torch.int64, random_grid_orient=True):
+        self.config = config
+        self.device = torch.device(device)
+        self.index_dtype = index_dtype
+        self.random_grid_orient = random_grid_orient
+        self.stream = torch.cuda.Stream(self.device)
+        # workspaces / inputs last touched on the training stream must be complete before first use here
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self._pending = None
+
+    def submit(self, make_inputs):
+        if self._pending is not None:
+            raise RuntimeError("PyramidPrefetcher.submit: the previous pyramid was not taken")
+        with torch.cuda.stream(self.stream):
+            points, lengths, extras = make_inputs()
+            pyr = build_pyramid(points, lengths, self.config, random_grid_orient=self.random_grid_orient,
+                                index_dtype=self.index_dtype)
+            ready = torch.cuda.Event()
+            ready.record(self.stream)
+        self._pending = (pyr, extras, ready)
+
+    def take(self):
+        if self._pending is None:
+            raise RuntimeError("PyramidPrefetcher.take: nothing was submitted")
+        pyr, extras, ready = self._pending
+        self._pending = None
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ready)
+        seen = set()
+
+        def mark(obj):
+            if isinstance(obj, torch.Tensor):
+                if obj.is_cuda and obj.data_ptr() not in seen:
+                    seen.add(obj.data_ptr())
+                    obj.record_stream(cur)
+            elif isinstance(obj, (list, tuple)):
+                for o in obj:
+                    mark(o)
+            elif isinstance(obj, dict):
+                mark(list(obj.values()))
+            elif isinstance(obj, SimpleNamespace):
+                mark(list(vars(obj).values()))
+        mark(pyr)
+        mark(extras)
+        return pyr, extras
