@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/mvk.h"
 
@@ -35,6 +36,52 @@ inline int cuda_fail(cudaError_t e, const char* what) {
     } while (0)
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Programmatic dependent launch.  The step is ~760 short launches back to back; a kernel launched through
+// launch_pdl may be scheduled while its predecessor in the stream is still draining, runs its prologue,
+// and blocks in pdl_enter() until the predecessor has completed and its writes are visible.  pdl_enter()
+// must therefore precede the first global-memory access of EVERY thread of a kernel launched this way
+// (it is a no-op under a plain launch).  It releases the next launch only after its own wait, so at most
+// one generation of CTAs is ever parked on the SMs.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+inline bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MVK_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
+}
+// cluster > 1: (cluster, 1, 1) thread-block clusters.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              int cluster, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (cluster > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        n++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // Bump allocator over the caller's workspace.
 struct Arena {

@@ -198,6 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_enter();  // barriers, TMEM and tensor-map prefetch are set up while the previous kernel drains
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -579,9 +580,16 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int a_mn_major, int lda
     if (auto_split && p.splits > 1)
         MVK_CUDA(cudaMemset2DAsync(D, (size_t)ldd * 4, 0, (size_t)n_valid * 4, (size_t)M, (cudaStream_t)stream));
     const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + staging_bytes;
-    MVK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
+    static thread_local int attr_dev = -1;  // the opt-in shared-memory limit is per device: set it once
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (attr_dev != cur_dev) {
+        MVK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT - 1024));
+        attr_dev = cur_dev;
+    }
     int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-    gemm_tc_kernel<<<grid, 64 + 32 * p.ew, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, md, p);
+    launch_pdl(gemm_tc_kernel, dim3(grid), dim3(64 + 32 * p.ew), smem, (cudaStream_t)stream, 1, ma_hi, ma_lo, mb_hi, mb_lo,
+               md, p);
     MVK_LAUNCHED("gemm_tc_kernel");
     if (col_stats && !p.col_stats) return mvk_col_stats(D, M, n_valid, ldd, col_stats, stream);
     return MVK_OK;

@@ -113,6 +113,7 @@ template <typename IdxT, int V>
 __global__ void __launch_bounds__(256)
 kp_weighted_fwd(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                 __nv_bfloat16* __restrict__ out_lo, int hcap) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     float* s_kp = (float*)smem_raw;  // [KP_MAX*3]
@@ -204,6 +205,7 @@ kp_weighted_fwd(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict
 template <typename IdxT, int V>
 __global__ void __launch_bounds__(256)
 kp_weighted_bwd(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx, int hcap) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     float* s_kp = (float*)smem_raw;
@@ -270,6 +272,7 @@ kp_weighted_bwd(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx, 
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ src, int rows, int cols, int src_ld,
                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int rows_pad, int ld) {
+    pdl_enter();
     size_t total = (size_t)rows_pad * ld;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (size_t)gridDim.x * blockDim.x) {
@@ -285,6 +288,7 @@ split_bf16_kernel(const float* __restrict__ src, int rows, int cols, int src_ld,
 __global__ void __launch_bounds__(256)
 split_bf16_vec4(const float* __restrict__ src, int rows, int cv, int src_ld, __nv_bfloat16* __restrict__ hi,
                 __nv_bfloat16* __restrict__ lo) {
+    pdl_enter();
     const size_t total = (size_t)rows * cv;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(t / cv), c = (int)(t % cv) * 4;
@@ -306,6 +310,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pool_fwd(const float* __restrict__ x, int ns, int c, const void* __restrict__ inds, int nq, int h,
          int mode, float* __restrict__ out, int* __restrict__ arg) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < nq; i += gridDim.x * wpb) {
         for (int ch = lane; ch < c; ch += 32) {
@@ -338,6 +343,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pool_fwd_vec4(const float* __restrict__ x, int ns, int c, const void* __restrict__ inds, int nq, int h,
               int mode, float* __restrict__ out, int* __restrict__ arg) {
+    pdl_enter();
     const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
     const int ncg = (c + 127) / 128;  // work item = (query, group of 128 channels): deep layers have few queries
     const long long items = (long long)nq * ncg;
@@ -370,6 +376,7 @@ template <typename IdxT>
 __global__ void __launch_bounds__(256)
 pool_bwd(const float* __restrict__ go, int ldg, int nq, int c, const int* __restrict__ arg,
          const void* __restrict__ inds, int h, int mode, int ns, float* __restrict__ gx) {
+    pdl_enter();
     size_t total = (size_t)nq * c;
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (size_t)gridDim.x * blockDim.x) {
@@ -446,6 +453,7 @@ template <typename IdxT, int G, int HCAP>
 __global__ void __launch_bounds__(256)
 kp_fwd_fast(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
             __nv_bfloat16* __restrict__ out_lo) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SUB = 32 / G;
     constexpr int CW = G * 4;
@@ -554,6 +562,7 @@ template <typename IdxT, int CIN>
 __global__ void __launch_bounds__(128)
 kp_fwd_tiny(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
             __nv_bfloat16* __restrict__ out_lo) {
+    pdl_enter();
     __shared__ float4 s_kc[KF];
     stage_kp_constants(a, s_kc);
     const float inv_ext = 1.f / a.extent;
@@ -634,6 +643,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <typename IdxT, int G, int HCAP>
 __global__ void __launch_bounds__(256)
 kp_bwd_fast(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx) {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int SUB = 32 / G;
     constexpr int CW = G * 4;  // channels per pass
@@ -770,7 +780,7 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
     if (tiny_ok(cin, num_kp, influence, aggregation)) {
         const int threads = 128, blocks_t = (nq + threads - 1) / threads;
 #define LAUNCH_TINY(IDX, C)                                                                          \
-    kp_fwd_tiny<IDX, C><<<blocks_t, threads, 0, st>>>(a, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo)
+    launch_pdl(kp_fwd_tiny<IDX, C>, dim3(blocks_t), dim3(threads), 0, st, 1, a, out_f32, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo)
 #define LAUNCH_TINY_C(IDX)                                                                           \
     do {                                                                                             \
         if (cin == 1) LAUNCH_TINY(IDX, 1);                                                           \
@@ -800,7 +810,7 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
     do {                                                                                             \
         auto kern = kp_fwd_fast<IDX, GG, HH>;                                                        \
         MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-        kern<<<blocks_f, wpb_f * 32, smem_f, st>>>(a, out_f32, (__nv_bfloat16*)out_hi,               \
+        launch_pdl(kern, dim3(blocks_f), dim3(wpb_f * 32), smem_f, st, 1, a, out_f32, (__nv_bfloat16*)out_hi,               \
                                                    (__nv_bfloat16*)out_lo);                          \
     } while (0)
 #define LAUNCH_FAST_G(IDX, HH)                                                                       \
@@ -838,7 +848,7 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
     do {                                                                                             \
         auto kern = kp_weighted_fwd<IDX, VV>;                                                        \
         MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<blocks, wpb * 32, smem, st>>>(a, out_f32, (__nv_bfloat16*)out_hi,                     \
+        launch_pdl(kern, dim3(blocks), dim3(wpb * 32), smem, st, 1, a, out_f32, (__nv_bfloat16*)out_hi,                     \
                                              (__nv_bfloat16*)out_lo, hcap);                          \
     } while (0)
     if (idx_is_i64) {
@@ -883,7 +893,7 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
     do {                                                                                             \
         auto kern = kp_bwd_fast<IDX, GG, HH>;                                                        \
         MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f)); \
-        kern<<<blocks_f, wpb_f * 32, smem_f, st_f>>>(a, grad_weighted, grad_x);                      \
+        launch_pdl(kern, dim3(blocks_f), dim3(wpb_f * 32), smem_f, st_f, 1, a, grad_weighted, grad_x);                      \
     } while (0)
 #define LAUNCH_FASTB_G(IDX, HH)                                                                      \
     do {                                                                                             \
@@ -918,7 +928,7 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
     do {                                                                                             \
         auto kern = kp_weighted_bwd<IDX, VV>;                                                        \
         MVK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kern<<<blocks, wpb * 32, smem, st>>>(a, grad_weighted, grad_x, hcap);                        \
+        launch_pdl(kern, dim3(blocks), dim3(wpb * 32), smem, st, 1, a, grad_weighted, grad_x, hcap);                        \
     } while (0)
     if (idx_is_i64) {
         if (V == 4) LAUNCH_BWD(long long, 4);
@@ -944,7 +954,7 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
         (((size_t)hi | (size_t)lo) & 7) == 0) {
         const size_t nv = (size_t)rows * (cols / 4);
         size_t nb = (nv + 255) / 256, mb = (size_t)num_sms() * 16;
-        split_bf16_vec4<<<(int)(nb < mb ? nb : mb), 256, 0, (cudaStream_t)stream>>>(
+        launch_pdl(split_bf16_vec4, dim3((int)(nb < mb ? nb : mb)), dim3(256), 0, (cudaStream_t)stream, 1, 
             src, rows, cols / 4, src_ld, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
         MVK_LAUNCHED("split_bf16_vec4");
         return MVK_OK;
@@ -952,7 +962,7 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
     int blocks = (int)((total + 255) / 256);
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;
-    split_bf16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, src_ld,
+    launch_pdl(split_bf16_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, src, rows, cols, src_ld,
                                                                 (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
                                                                 rows_pad, ld);
     MVK_LAUNCHED("split_bf16");
@@ -970,13 +980,13 @@ int mvk_pool(const float* x, int ns, int c, const void* inds, int idx_is_i64, in
         const long long items = (long long)nq * ((c + 127) / 128);
         blocks = (int)((items + 7) / 8 < (long long)maxb ? (items + 7) / 8 : maxb);
         if (idx_is_i64)
-            pool_fwd_vec4<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+            launch_pdl(pool_fwd_vec4<long long>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, x, ns, c, inds, nq, h, mode, out, arg_out);
         else
-            pool_fwd_vec4<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+            launch_pdl(pool_fwd_vec4<int>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, x, ns, c, inds, nq, h, mode, out, arg_out);
     } else if (idx_is_i64)
-        pool_fwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+        launch_pdl(pool_fwd<long long>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, x, ns, c, inds, nq, h, mode, out, arg_out);
     else
-        pool_fwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ns, c, inds, nq, h, mode, out, arg_out);
+        launch_pdl(pool_fwd<int>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, x, ns, c, inds, nq, h, mode, out, arg_out);
     MVK_LAUNCHED("pool_fwd");
     return MVK_OK;
 }
@@ -991,9 +1001,9 @@ int mvk_pool_bwd(const float* grad_out, int ldg, int nq, int c, const int* arg, 
     int maxb = num_sms() * 16;
     if (blocks > maxb) blocks = maxb;
     if (idx_is_i64)
-        pool_bwd<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ldg, nq, c, arg, inds, h, mode, ns, grad_x);
+        launch_pdl(pool_bwd<long long>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, grad_out, ldg, nq, c, arg, inds, h, mode, ns, grad_x);
     else
-        pool_bwd<int><<<blocks, 256, 0, (cudaStream_t)stream>>>(grad_out, ldg, nq, c, arg, inds, h, mode, ns, grad_x);
+        launch_pdl(pool_bwd<int>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, 1, grad_out, ldg, nq, c, arg, inds, h, mode, ns, grad_x);
     MVK_LAUNCHED("pool_bwd");
     return MVK_OK;
 }

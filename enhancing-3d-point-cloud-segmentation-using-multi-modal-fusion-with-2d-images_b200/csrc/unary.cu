@@ -164,6 +164,7 @@ template <int VEC>
 __global__ void __launch_bounds__(TB)
 col_stats_kernel(const float* __restrict__ y, int rows, int cols, int ld, double* __restrict__ stats, int rows_per_cta,
                  BnFin fin) {
+    pdl_enter();
     __shared__ float red[2 * TB * VEC];
     __shared__ float csum[2 * 32 * VEC];
     __shared__ unsigned int s_last;
@@ -268,6 +269,7 @@ scale_shift_act_kernel(const float* __restrict__ y, int rows, int cols, int ld, 
                        const float* __restrict__ shift, const float* __restrict__ residual, int ldr, float slope,
                        float* __restrict__ out, int ldo, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                        int ldh) {
+    pdl_enter();
     const int cv = cols / VEC;
     const size_t total = (size_t)rows * cv;
     for (size_t t = (size_t)blockIdx.x * TB + threadIdx.x; t < total; t += (size_t)gridDim.x * TB) {
@@ -305,6 +307,7 @@ act_bwd_reduce_kernel(const float* __restrict__ dz, int lddz, const float* __res
                       const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ residual, int ldr, const float* __restrict__ mean,
                       const float* __restrict__ invstd, float slope, double* __restrict__ sums, int rows_per_cta) {
+    pdl_enter();
     __shared__ float red[2 * TB * VEC];
     __shared__ float csum[2 * 32 * VEC];
     const Map2D m = make_map2d(cols, VEC);
@@ -366,6 +369,7 @@ act_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __rest
                      float* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                      int ldh, float* __restrict__ dres, int lddres, float* __restrict__ dgamma,
                      float* __restrict__ dbeta) {
+    pdl_enter();
     if (blockIdx.x == 0 && sums) {
         for (int c = threadIdx.x; c < cols; c += TB) {
             if (dbeta) dbeta[c] = (float)sums[c];
@@ -429,23 +433,6 @@ inline int slab_rows(int rows, int cols, int vec, dim3* grid, int* cluster) {
     *grid = dim3(gx, ncg, 1);
     return rpc;
 }
-// Launch with a (cluster, 1, 1) thread-block cluster.
-template <typename... KArgs, typename... Args>
-inline void launch_clustered(void (*kernel)(KArgs...), dim3 grid, int cluster, cudaStream_t stream, Args... args) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(TB, 1, 1);
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
-}
 inline int ew_grid(size_t total) {
     size_t b = (total + TB - 1) / TB;
     size_t maxb = (size_t)num_sms() * 16;
@@ -467,8 +454,8 @@ int mvk_col_stats(const float* y, int rows, int cols, int ld, double* stats, mvk
     int cl;
     const int rpc = slab_rows(rows, cols, vec, &grid, &cl);
     BnFin fin = {};
-    if (vec == 4) launch_clustered(col_stats_kernel<4>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
-    else launch_clustered(col_stats_kernel<1>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
+    if (vec == 4) launch_pdl(col_stats_kernel<4>, grid, dim3(TB), 0, (cudaStream_t)stream, cl, y, rows, cols, ld, stats, rpc, fin);
+    else launch_pdl(col_stats_kernel<1>, grid, dim3(TB), 0, (cudaStream_t)stream, cl, y, rows, cols, ld, stats, rpc, fin);
     MVK_LAUNCHED("col_stats");
     return MVK_OK;
 }
@@ -484,8 +471,8 @@ int mvk_bn_batch_stats(const float* y, int rows, int cols, int ld, double* stats
     const int rpc = slab_rows(rows, cols, vec, &grid, &cl);
     BnFin fin = {gamma, beta, eps, momentum, running_mean, running_var, scale, shift, mean_out, invstd_out,
                  (unsigned int*)(stats + 2 * (size_t)cols), num_batches_tracked};
-    if (vec == 4) launch_clustered(col_stats_kernel<4>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
-    else launch_clustered(col_stats_kernel<1>, grid, cl, (cudaStream_t)stream, y, rows, cols, ld, stats, rpc, fin);
+    if (vec == 4) launch_pdl(col_stats_kernel<4>, grid, dim3(TB), 0, (cudaStream_t)stream, cl, y, rows, cols, ld, stats, rpc, fin);
+    else launch_pdl(col_stats_kernel<1>, grid, dim3(TB), 0, (cudaStream_t)stream, cl, y, rows, cols, ld, stats, rpc, fin);
     MVK_LAUNCHED("col_stats+finalize");
     return MVK_OK;
 }
@@ -512,11 +499,11 @@ int mvk_scale_shift_act(const float* y, int rows, int cols, int ld, const float*
     const int vec = vec_for(cols, ld, residual ? ldr : 4, out ? ldo : 4, out_hi ? ldh : 4);
     const int grid = ew_grid((size_t)rows * (cols / vec));
     if (vec == 4)
-        scale_shift_act_kernel<4><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, scale, shift, residual, ldr,
+        launch_pdl(scale_shift_act_kernel<4>, dim3(grid), dim3(TB), 0, (cudaStream_t)stream, 1, y, rows, cols, ld, scale, shift, residual, ldr,
                                                                         slope, out, ldo, (__nv_bfloat16*)out_hi,
                                                                         (__nv_bfloat16*)out_lo, ldh);
     else
-        scale_shift_act_kernel<1><<<grid, TB, 0, (cudaStream_t)stream>>>(y, rows, cols, ld, scale, shift, residual, ldr,
+        launch_pdl(scale_shift_act_kernel<1>, dim3(grid), dim3(TB), 0, (cudaStream_t)stream, 1, y, rows, cols, ld, scale, shift, residual, ldr,
                                                                         slope, out, ldo, (__nv_bfloat16*)out_hi,
                                                                         (__nv_bfloat16*)out_lo, ldh);
     MVK_LAUNCHED("scale_shift_act");
@@ -534,10 +521,10 @@ int mvk_act_bwd_reduce(const float* dz, int lddz, const float* y, int rows, int 
     int cl;
     const int rpc = slab_rows(rows, cols, vec, &grid, &cl);
     if (vec == 4)
-        launch_clustered(act_bwd_reduce_kernel<4>, grid, cl, (cudaStream_t)stream, dz, lddz, y, rows, cols, ld, scale,
+        launch_pdl(act_bwd_reduce_kernel<4>, grid, dim3(TB), 0, (cudaStream_t)stream, cl, dz, lddz, y, rows, cols, ld, scale,
                          shift, residual, ldr, mean, invstd, slope, sums, rpc);
     else
-        launch_clustered(act_bwd_reduce_kernel<1>, grid, cl, (cudaStream_t)stream, dz, lddz, y, rows, cols, ld, scale,
+        launch_pdl(act_bwd_reduce_kernel<1>, grid, dim3(TB), 0, (cudaStream_t)stream, cl, dz, lddz, y, rows, cols, ld, scale,
                          shift, residual, ldr, mean, invstd, slope, sums, rpc);
     MVK_LAUNCHED("act_bwd_reduce");
     return MVK_OK;
@@ -557,12 +544,12 @@ int mvk_act_bwd_apply(const float* dz, int lddz, const float* y, int rows, int c
         if (vec == 4 && ((dy_hi && ldh % 4 != 0) || (dres && lddres % 4 != 0))) vec = 1;
         const int grid = ew_grid((size_t)rows * (cols / vec));
         if (vec == 4)
-            act_bwd_apply_kernel<4><<<grid, TB, 0, st>>>(dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
+            launch_pdl(act_bwd_apply_kernel<4>, dim3(grid), dim3(TB), 0, st, 1, dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
                                                          invstd, slope, sums, batch_stats, dy, lddy,
                                                          (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres,
                                                          dgamma, dbeta);
         else
-            act_bwd_apply_kernel<1><<<grid, TB, 0, st>>>(dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
+            launch_pdl(act_bwd_apply_kernel<1>, dim3(grid), dim3(TB), 0, st, 1, dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
                                                          invstd, slope, sums, batch_stats, dy, lddy,
                                                          (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres,
                                                          dgamma, dbeta);

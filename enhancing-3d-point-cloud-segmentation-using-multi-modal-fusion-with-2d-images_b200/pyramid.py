@@ -170,7 +170,9 @@ class PyramidPrefetcher:
         self.device = torch.device(device)
         self.index_dtype = index_dtype
         self.random_grid_orient = random_grid_orient
-        self.stream = torch.cuda.Stream(self.device)
+        # high priority: the pyramid's short kernels must not queue behind the training backlog, or each of
+        # its size read-backs would stall the host for as long as that backlog takes to drain
+        self.stream = torch.cuda.Stream(self.device, priority=-1)
         # workspaces / inputs last touched on the training stream must be complete before first use here
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self._pending = None
