@@ -10,56 +10,7 @@ from . import build as _build
 
 _LIB = None
 
-vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t
-
-# name -> (restype, argtypes); mirrors include/mvk.h one to one.
-SIGNATURES = {
-    "mvk_error_string": (C.c_char_p, [i32]),
-    "mvk_last_cuda_error": (C.c_char_p, []),
-    "mvk_version": (i32, []),
-    "mvk_launch_count": (C.c_ulonglong, []),
-    "mvk_free_host": (None, [vp]),
-    "mvk_neighbors_workspace_bytes": (sz, [i32, i32, i32]),
-    "mvk_neighbors_count": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, vp, vp, vp]),
-    "mvk_neighbors_fill": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, vp]),
-    "mvk_neighbors_fill_i64": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, vp]),
-    "mvk_neighbors_query_capped": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, vp, sz, i32, i32, vp, i32, vp, vp, i32, vp]),
-    "mvk_batch_neighbors_host": (i32, [vp, i32, vp, i32, vp, vp, i32, f32, C.POINTER(vp), C.POINTER(i32)]),
-    "mvk_subsample_workspace_bytes": (sz, [i32, i32, i32, i32]),
-    "mvk_grid_subsample": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, vp, sz, vp, vp, vp, vp, vp, vp]),
-    "mvk_rotate_batch": (i32, [vp, i32, vp, i32, vp, i32, vp, vp]),
-    "mvk_grid_subsample_host": (i32, [vp, i32, vp, i32, vp, i32, vp, i32, f32, i32, C.POINTER(vp),
-                                      C.POINTER(vp), C.POINTER(vp), vp, C.POINTER(i32)]),
-    "mvk_kpconv_weighted": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, i32, f32, i32, i32, i32,
-                                  vp, vp, vp, vp]),
-    "mvk_kpconv_weighted_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, i32, vp, i32, f32, i32, i32, vp,
-                                      i32, vp, vp]),
-    "mvk_kpconv_deform_weighted": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, vp, i32, f32, i32, i32, i32,
-                                         vp, vp, vp, vp, vp, vp]),
-    "mvk_kpconv_deform_weighted_bwd": (i32, [vp, i32, vp, i32, vp, i32, i32, vp, i32, vp, vp, i32, f32, i32, i32, vp,
-                                             i32, vp, vp, vp, vp, vp, vp]),
-    "mvk_split_bf16": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp]),
-    "mvk_gemm_bf16x3": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp]),
-    "mvk_gemm_bf16x3_stats": (i32, [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, i32, i32, vp, vp]),
-    "mvk_gemm_f32": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp, i32, i32, vp]),
-    "mvk_col_stats": (i32, [vp, i32, i32, i32, vp, vp]),
-    "mvk_bn_batch_stats": (i32, [vp, i32, i32, i32, vp, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "mvk_bn_finalize": (i32, [vp, i32, i32, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "mvk_scale_shift_act": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, f32, vp, i32, vp, vp, i32, vp]),
-    "mvk_act_bwd_reduce": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, vp, vp]),
-    "mvk_act_bwd_apply": (i32, [vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, f32, vp, i32, vp, i32, vp, vp,
-                                i32, vp, i32, vp, vp, vp]),
-    "mvk_pool": (i32, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
-    "mvk_pool_bwd": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, vp]),
-    "mvk_unproject_views": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
-    "mvk_knn_workspace_bytes": (sz, [i32, i32]),
-    "mvk_knn_pixels": (i32, [vp, vp, i32, vp, i32, i32, vp, sz, vp, vp]),
-    "mvk_group_points": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp]),
-    "mvk_group_points_bwd": (i32, [vp, i32, i32, i32, vp, i32, i32, vp, vp]),
-    "mvk_fa_layer": (i32, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
-    "mvk_fa_gather": (i32, [vp, i64, i64, i32, vp, vp, i32, i32, vp, vp, i32, vp]),
-    "mvk_fa_reduce": (i32, [vp, i32, i32, i32, vp, vp, i32, vp, vp]),
-}
+from ._abi import SIGNATURES, vp, i32, i64, f32, sz  # noqa: F401  (name -> (restype, argtypes))
 
 
 def lib_path():
@@ -110,6 +61,30 @@ class profile:
         return False
 
 
+class _FastLib:
+    """The library handle the ops call through.  Entry points whose arguments are all plain pointers,
+    integers and floats are bound through the generated CPython shim (_mvkcall, METH_FASTCALL: ~0.4 us
+    per call instead of ~5 us of ctypes marshalling for a 25-argument launch -- the step makes ~450
+    such calls); everything else, and everything when the shim is unavailable, goes through ctypes.
+    Either way the callee is the same C-ABI function of libmvk.so."""
+
+    def __init__(self, handle):
+        self._handle = handle
+        fast = None
+        if os.environ.get("MVK_FASTCALL", "1") != "0":
+            try:
+                from . import _mvkcall as fast  # built next to libmvk.so by build.py
+            except ImportError:
+                fast = None
+        self._fast = fast
+        for name in SIGNATURES:
+            fn = getattr(fast, name, None) if fast is not None else None
+            setattr(self, name, fn if fn is not None else getattr(handle, name))
+
+    def __getattr__(self, name):  # symbols outside SIGNATURES
+        return getattr(self._handle, name)
+
+
 def lib():
     """Load (building first if stale and nvcc is present).  Raises if the CUDA library is unavailable."""
     global _LIB
@@ -127,7 +102,7 @@ def lib():
             fn = getattr(handle, name)  # AttributeError = header/library mismatch: fail loudly
             fn.restype = res
             fn.argtypes = args
-        _LIB = handle
+        _LIB = _FastLib(handle)
     if _PROFILE_RECORDS is not None:
         return _ProfiledLib(_LIB, _PROFILE_RECORDS)
     return _LIB

@@ -39,6 +39,33 @@ def test_library_is_sm100a_with_tcgen05_and_tma(mvk):
     assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
 
 
+def test_fastcall_shim_mirrors_the_ctypes_binding(mvk):
+    """The generated CPython shim (_mvkcall) binds the same C-ABI functions as ctypes: every entry point made
+    of pointers / integers / floats is present, argument checking happens in the callee (same return code
+    through both bindings), and bad Python arguments raise instead of reaching the library."""
+    import ctypes as C
+    mvk.build.build()
+    L = mvk._lib.lib()
+    fast = L._fast
+    assert fast is not None, "_mvkcall.so was not built (gcc / Python.h missing?)"
+    plain = {C.c_void_p, C.c_int, C.c_longlong, C.c_size_t, C.c_float, C.c_double}
+    expected = [n for n, (res, args) in mvk._lib.SIGNATURES.items() if res is C.c_int and all(a in plain for a in args)]
+    assert len(expected) >= 25
+    for n in expected:
+        assert hasattr(fast, n), n
+        assert getattr(L, n) is getattr(fast, n)
+    handle = L._handle
+    args = (0, 4, 0, 0, 8, 8, 0, 0, None, 8, 0, 0, 0.1, 0, 1, None, 0, 0, 0, 8, None, 8, None, None, 0)
+    assert fast.mvk_act_bwd_apply(*args) == handle.mvk_act_bwd_apply(*args) == -1  # MVK_ERR_INVALID_ARG
+    assert fast.mvk_split_bf16(None, np.int64(4), 4, 4, None, None, 4, 8, None) == handle.mvk_split_bf16(
+        None, 4, 4, 4, None, None, 4, 8, None)
+    with pytest.raises(TypeError):
+        fast.mvk_split_bf16(None, 4, 4)              # wrong arity
+    with pytest.raises(TypeError):
+        fast.mvk_split_bf16("x", 4, 4, 4, None, None, 4, 8, None)  # not a pointer
+    assert fast.mvk_version() == handle.mvk_version()
+
+
 def test_error_strings_and_version(mvk):
     L = mvk._lib.lib()
     assert L.mvk_version() >= 100
