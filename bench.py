@@ -186,9 +186,9 @@ def run_b200(args):
         loss.backward()
         if world > 1 and not use_ddp:
             allreduce_grads()
-        torch.nn.utils.clip_grad_value_(net.parameters(), 100.0)  # utils/trainer.py:191-193
+        torch.nn.utils.clip_grad_value_(grad_params, 100.0)  # utils/trainer.py:191-193
         opt.step()
-        return loss
+        return loss.detach()
 
     def step(from_host):
         """One un-pipelined step (profiling passes and --no-prefetch): pyramid, then training, one stream."""

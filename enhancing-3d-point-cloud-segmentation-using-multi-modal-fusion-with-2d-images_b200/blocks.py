@@ -369,3 +369,53 @@ class UnaryBlock(nn.Module):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(self.in_dim, self.out_dim,
                                                                                         str(self.use_bn),
                                                                                         str(not self.no_relu))
+
+
+# -------------------------------------------------------------------------------------------------
+class _SoftmaxXent(torch.autograd.Function):
+    """mean_{valid rows} (logsumexp(x_r) - x_r[label_r]); KPFCNN.loss, architectures.py:352-373."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if not logits.is_cuda:
+            raise RuntimeError("softmax_cross_entropy: tensors must live on a CUDA device (no CPU fallback)")
+        x = _f32c(logits)
+        y = labels.to(torch.int64).contiguous()
+        rows, classes = x.shape
+        dev = x.device
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        lse = torch.empty(max(rows, 1), dtype=torch.float32, device=dev)
+        with _lib.on_device(dev):
+            acc = _lib.zeros_ptr(16, dev)  # [loss sum f64][valid rows u32][ticket u32]
+            if rows > 0:
+                check(L.mvk_softmax_xent(x.data_ptr(), classes, y.data_ptr(), rows, classes, int(ignore_index),
+                                         lse.data_ptr(), acc, acc + 8, out.data_ptr(), stream_ptr()))
+            else:
+                out.fill_(float("nan"))
+        ctx.save_for_backward(x, y, lse)
+        ctx.cfg = (rows, classes, int(ignore_index), acc + 8, _lib._ZEROS.buf)  # the pool chunk stays alive
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        x, y, lse = ctx.saved_tensors
+        rows, classes, ignore_index, count, _keep = ctx.cfg
+        dev = x.device
+        grad = torch.empty_like(x)
+        if rows > 0:
+            gu = g.to(torch.float32).contiguous()
+            with _lib.on_device(dev):
+                check(L.mvk_softmax_xent_bwd(x.data_ptr(), classes, y.data_ptr(), rows, classes, ignore_index,
+                                             lse.data_ptr(), count, gu.data_ptr(), grad.data_ptr(), classes,
+                                             stream_ptr()))
+        return grad, None, None
+
+
+def softmax_cross_entropy(logits, labels, ignore_index=-1):
+    """``torch.nn.CrossEntropyLoss(ignore_index=ignore_index)(logits.T.unsqueeze(0), labels.unsqueeze(0))`` --
+    the way KPFCNN.loss calls it (architectures.py:352-373) -- on [N, C] logits and [N] labels: one
+    forward and one backward kernel."""
+    return _SoftmaxXent.apply(logits, labels, ignore_index)

@@ -157,6 +157,8 @@ class KPFCNN(nn.Module):
 
     def __init__(self, config, num_classes=None, ops=None):
         super().__init__()
+        self._product_ops = ops is None  # the CPU oracle graph (tests, bench cpu_baseline) injects its own ops
+        self._has_deformable = None
         ops = ops or product_ops()
         arch = config.architecture
         layer, r = 0, config.first_subsampling_dl * config.conv_radius
@@ -209,8 +211,13 @@ class KPFCNN(nn.Module):
         return self.head_softmax(self.head_mlp(x, batch), batch)
 
     def loss(self, outputs, labels):
-        loss = self.criterion(outputs.transpose(0, 1).unsqueeze(0), labels.unsqueeze(0))
-        if any(getattr(m, "deformable", False) for m in self.kpconv_layers()):
+        if self._product_ops and outputs.is_cuda:
+            loss = _blocks.softmax_cross_entropy(outputs, labels, ignore_index=-1)
+        else:
+            loss = self.criterion(outputs.transpose(0, 1).unsqueeze(0), labels.unsqueeze(0))
+        if self._has_deformable is None:
+            self._has_deformable = any(getattr(m, "deformable", False) for m in self.kpconv_layers())
+        if self._has_deformable:
             loss = loss + self.fitting_regularizer()
         return loss
 

@@ -246,6 +246,19 @@ int mvk_act_bwd_apply(const float* dz, int lddz, const float* y, int rows, int c
                       void* dy_lo_bf16, int ldh, float* dres, int lddres, float* dgamma, float* dbeta,
                       mvk_stream_t stream);
 
+/* Segmentation loss of the KPFCNN head (architectures.py:176-181, 352-373: CrossEntropyLoss(ignore_index=-1)
+ * on [rows, classes] logits, mean over the valid rows).  Forward: lse [rows] receives the per-row
+ * log-sum-exp (kept for the backward), loss_acc (1 double) and count (2 uints: valid rows, retirement
+ * ticket) must be zero-initialised, loss_out (1 float, device) receives the mean (NaN if no row is valid).
+ * Backward: grad [rows, ldg] = (softmax - onehot) * upstream[0] / valid, zero rows for ignored labels;
+ * upstream is a DEVICE scalar (no host read-back). */
+int mvk_softmax_xent(const float* logits, int ld, const long long* labels, int rows, int classes,
+                     long long ignore_index, float* lse, double* loss_acc, unsigned int* count, float* loss_out,
+                     mvk_stream_t stream);
+int mvk_softmax_xent_bwd(const float* logits, int ld, const long long* labels, int rows, int classes,
+                         long long ignore_index, const float* lse, const unsigned int* count, const float* upstream,
+                         float* grad, int ldg, mvk_stream_t stream);
+
 /* Gather pools on the neighbour matrices (blocks.py:79-110): mode 0 = max_pool (zero-padded
  * shadow row!), 1 = closest_pool (first column).  arg_out [nq, c] i32 (max_pool only) records the
  * winning support row for the backward.  Backward: grad_x[arg] += grad_out. */

@@ -25,7 +25,21 @@ SHAPES = [  # M, N, K, a_mn, b_mn, split, tag
 ]
 
 def main():
-    ap = argparse.ArgumentParser(); ap.add_argument("--reps", type=int, default=5); ap.add_argument("--only", default=""); args = ap.parse_args()
+    ap = argparse.ArgumentParser(); ap.add_argument("--reps", type=int, default=5); ap.add_argument("--only", default="")
+    ap.add_argument("--from-json", default="", help="bench.py --detail N output: time every contraction shape of the step")
+    args = ap.parse_args()
+    calls = {}
+    if args.from_json:
+        import re
+        d = json.loads(open(args.from_json).read().strip().splitlines()[-1])["detail_us_per_call"]
+        SHAPES[:] = []
+        for k, (us, n) in d.items():
+            m = re.match(r"mvk_gemm_bf16x3\[M=(\d+),N=(\d+),K=(\d+),amn=(\d),bmn=(\d),split=(\d+)\]", k)
+            if m:
+                M, N, K, amn, bmn, split = map(int, m.groups())
+                tag = f"step x{n} ({us:.1f} us in situ)"
+                SHAPES.append((M, N, K, amn, bmn, split, tag))
+                calls[tag + str((M, N, K, amn, bmn))] = n
     import mvkpconv_b200 as mvk
     from mvkpconv_b200._lib import check, ptr, stream_ptr
     L = mvk._lib.lib()
@@ -68,7 +82,7 @@ def main():
         nbytes = 4.0 * (M * K + K * N) + 4.0 * M * N
         flops = 6.0 * M * N * K
         ideal = max(nbytes / hbm, flops / tc) * 1e6
-        tot += us
+        tot += us * calls.get(tag + str((M, N, K, amn, bmn)), 1)
         print(f"{us:8.1f} us  ideal {ideal:7.1f}  frac {ideal/us:5.2f}  {nbytes/us/1e3:7.0f} GB/s {flops/us/1e6:7.1f} TF/s  M={M} N={N} K={K} amn={amn} bmn={bmn} split={split}  {tag}", flush=True)
     print("total us", round(tot, 1))
 

@@ -133,3 +133,31 @@ def test_gemm_fused_column_statistics(mvk):
         assert rel_err(D, ref) < 2e-5
         assert rel_err(stats[:N], ref.sum(0)) < 1e-4, (M, N, K)
         assert rel_err(stats[N:], (ref * ref).sum(0)) < 1e-4, (M, N, K)
+
+
+def test_softmax_cross_entropy_vs_torch(mvk):
+    """KPFCNN.loss (architectures.py:352-373): CrossEntropyLoss(ignore_index=-1) on the transposed logits.
+    Forward and gradient within 1e-5 relative of torch's fp32 implementation, incl. ignored rows, an
+    upstream gradient != 1, and the all-ignored case (NaN loss, zero gradient rows like torch)."""
+    import torch
+    g = torch.Generator().manual_seed(3)
+    for rows, classes in ((5000, 20), (33, 6), (1, 3), (70000, 13)):
+        x = (torch.randn(rows, classes, generator=g) * 3).cuda().requires_grad_(True)
+        y = torch.randint(0, classes, (rows,), generator=g)
+        y[torch.rand(rows, generator=g) < 0.2] = -1
+        y = y.cuda()
+        ref_x = x.detach().clone().requires_grad_(True)
+        ref = torch.nn.CrossEntropyLoss(ignore_index=-1)(ref_x.transpose(0, 1).unsqueeze(0), y.unsqueeze(0))
+        out = mvk.softmax_cross_entropy(x, y, ignore_index=-1)
+        (out * 1.7).backward()
+        (ref * 1.7).backward()
+        if bool((y >= 0).any()):
+            assert abs(out.item() - ref.item()) <= 1e-5 * max(1.0, abs(ref.item()))
+            assert float((x.grad - ref_x.grad).abs().max()) <= 1e-5 * float(ref_x.grad.abs().max()) + 1e-9
+        else:
+            assert np.isnan(out.item()) and np.isnan(ref.item())
+        assert float(x.grad[y < 0].abs().sum()) == 0.0
+    x = torch.randn(10, 4).cuda().requires_grad_(True)
+    y = torch.full((10,), -1).cuda()
+    out = mvk.softmax_cross_entropy(x, y)
+    assert np.isnan(out.item())
