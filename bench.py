@@ -150,8 +150,9 @@ def run_b200(args):
                                                           bucket_cap_mb=64)
     elif world > 1:
         # identical replicas to start with (DDP would broadcast rank 0's parameters and buffers)
-        for t in list(net.parameters()) + list(net.buffers()):
-            dist.broadcast(t.data, 0)
+        with torch.no_grad():  # in-place writes that move the version counters (the bf16 weight pairs key on them)
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t, 0)
     grad_params = [p for p in net.parameters() if p.requires_grad]
 
     def allreduce_grads():

@@ -22,7 +22,7 @@ import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
 
-from . import _lib
+from . import _lib, _weights
 from ._lib import check, ptr, stream_ptr
 from . import kpconv as _kp
 
@@ -199,11 +199,10 @@ class _LinearBNAct(torch.autograd.Function):
         cached = None if fp32 else _cached_hilo(x, rows, ldx)
         with _lib.on_device(dev):
             nx = 0 if (fp32 or cached is not None) else 2 * rows * ldx
-            nw = 0 if fp32 else 2 * cout * ldx
-            keep, (x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd, z_hi, z_lo) = _carve(
-                dev, nx, nx, nw, nw, 4 * rows * cout, *([4 * cout] * 4 if use_bn else [0] * 4),
+            keep, (x_hi, x_lo, y, sc, sh, mu, isd, z_hi, z_lo) = _carve(
+                dev, nx, nx, 4 * rows * cout, *([4 * cout] * 4 if use_bn else [0] * 4),
                 *([2 * rows * cout] * 2 if emit else [0, 0]))
-            xkeep = stats = None
+            xkeep = stats = wkeep = w_hi = w_lo = None
             if fp32:
                 if rows > 0:
                     check(L.mvk_gemm_f32(xf.data_ptr(), cin, 1, w.data_ptr(), 1, cin, rows, cout, cin, y, cout, 1, st))
@@ -214,7 +213,7 @@ class _LinearBNAct(torch.autograd.Function):
                 else:
                     check(L.mvk_split_bf16(xf.data_ptr(), rows, cin, cin, x_hi, x_lo, rows, ldx, st))
                     _attach_hilo(x, keep, x_hi, x_lo, rows, ldx)
-                check(L.mvk_split_bf16(w.data_ptr(), cout, cin, cin, w_hi, w_lo, cout, ldx, st))
+                w_hi, w_lo, wkeep, _ = _weights.weight_operands(w, cout, cin, cin, cout, ldx)  # once per optimiser step
                 if rows > 0 and use_bn and training and _FUSE_BN_STATS:
                     # batch statistics ride in the contraction's epilogue (measured: the extra epilogue work
                     # costs as much as the separate statistics pass it saves, so this is off by default)
@@ -229,9 +228,10 @@ class _LinearBNAct(torch.autograd.Function):
             z = torch.empty((rows, cout), dtype=torch.float32, device=dev)
             check(L.mvk_scale_shift_act(y, rows, cout, cout, sc, sh, ptr(res), cout, slope, z.data_ptr(), cout, z_hi, z_lo,
                                         cout, st))
-        ctx.save_for_backward(keep, xkeep, res, xf if fp32 else None, w if fp32 else None, beta if not use_bn else None)
+        # w is saved on every path: autograd's version check on it also guards its bf16 pair (wkeep)
+        ctx.save_for_backward(keep, xkeep, res, xf if fp32 else None, w, beta if not use_bn else None)
         ctx.cfg = (rows, cin, cout, use_bn, training, slope, gamma is not None, beta is not None, contraction, ldx,
-                   (x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd))
+                   (x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd), wkeep)
         if emit:
             _attach_hilo(z, keep, z_hi, z_lo, rows, cout)
         return z
@@ -240,7 +240,7 @@ class _LinearBNAct(torch.autograd.Function):
     def backward(ctx, dz):
         L = _lib.lib()
         keep, xkeep, res, xf, w, _bias = ctx.saved_tensors
-        rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction, ldx, ptrs = ctx.cfg
+        rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction, ldx, ptrs, _wkeep = ctx.cfg
         x_hi, x_lo, w_hi, w_lo, y, sc, sh, mu, isd = ptrs
         g, ldg = _rows_f32(dz)
         dev = g.device

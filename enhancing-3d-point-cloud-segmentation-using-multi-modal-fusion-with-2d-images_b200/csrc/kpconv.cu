@@ -305,6 +305,40 @@ split_bf16_vec4(const float* __restrict__ src, int rows, int cv, int src_ld, __n
     }
 }
 
+// Every weight matrix of a model in one launch (the parameters change once per optimiser step: one split
+// per step instead of one tiny launch per layer).  CTA b serves 4096 destination elements of the tensor
+// whose chunk range contains b.
+__global__ void __launch_bounds__(256)
+split_bf16_multi(const mvk_split_desc* __restrict__ table, int n) {
+    pdl_enter();
+    __shared__ int s_i;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (table[mid].first_chunk <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+        }
+        s_i = lo;
+    }
+    __syncthreads();
+    const mvk_split_desc d = table[s_i];
+    const size_t total = (size_t)d.rows_pad * d.dst_ld;  // dst_ld is even (16-byte row pitch)
+    const size_t base = (size_t)((int)blockIdx.x - d.first_chunk) * 4096;
+    const size_t end = base + 4096 < total ? base + 4096 : total;
+    __nv_bfloat16* hi = (__nv_bfloat16*)d.hi;
+    __nv_bfloat16* lo = (__nv_bfloat16*)d.lo;
+    for (size_t t = base + 2 * threadIdx.x; t < end; t += 512) {
+        const int r = (int)(t / d.dst_ld), c = (int)(t % d.dst_ld);
+        const float* row = d.src + (size_t)r * d.src_ld;
+        const float v0 = (r < d.rows && c < d.cols) ? row[c] : 0.f;
+        const float v1 = (r < d.rows && c + 1 < d.cols) ? row[c + 1] : 0.f;
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+        const float2 f = __bfloat1622float2(h);
+        *(__nv_bfloat162*)(hi + t) = h;
+        *(__nv_bfloat162*)(lo + t) = __floats2bfloat162_rn(v0 - f.x, v1 - f.y);
+    }
+}
+
 // mode 0: max over neighbours with a ZERO shadow row (blocks.py:93-110); mode 1: first column.
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
@@ -966,6 +1000,13 @@ int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, v
                                                                 (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
                                                                 rows_pad, ld);
     MVK_LAUNCHED("split_bf16");
+    return MVK_OK;
+}
+
+int mvk_split_bf16_multi(const mvk_split_desc* table_dev, int n_tensors, int total_chunks, mvk_stream_t stream) {
+    if (!table_dev || n_tensors < 1 || total_chunks < 1) return MVK_ERR_INVALID_ARG;
+    launch_pdl(split_bf16_multi, dim3(total_chunks), dim3(256), 0, (cudaStream_t)stream, 1, table_dev, n_tensors);
+    MVK_LAUNCHED("split_bf16_multi");
     return MVK_OK;
 }
 

@@ -25,7 +25,7 @@ import torch.nn as nn
 from torch.nn.init import kaiming_uniform_
 from torch.nn.parameter import Parameter
 
-from . import _lib
+from . import _lib, _weights
 from ._lib import check, ptr, stream_ptr
 from .kernel_points import load_kernels
 
@@ -101,17 +101,18 @@ class _KPConvFunction(torch.autograd.Function):
                 terms = 3 if contraction == "bf16x3" else 1
                 ld = _round_up(kd, 8)      # 16-byte row pitch is all TMA needs: partial tiles are zero-filled
                 npad = _round_up(cout, 8)
-                keep, (a_hi, a_lo, w_hi, w_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld, 2 * ld * npad, 2 * ld * npad)
+                keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld)
                 check(L.mvk_kpconv_weighted(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(), cin,
                                             kp.data_ptr(), K, float(kp_extent), influence, aggregation, ld, None, a_hi,
                                             a_lo, st))
-                check(L.mvk_split_bf16(w.data_ptr(), kd, cout, cout, w_hi, w_lo, ld, npad, st))
+                w_hi, w_lo, wkeep, _ = _weights.weight_operands(w, kd, cout, cout, ld, npad)  # once per optimiser step
                 if nq > 0:
                     check(L.mvk_gemm_bf16x3(a_hi, a_lo, 0, ld, w_hi, w_lo, 1, npad, nq, npad, ld, out.data_ptr(), cout,
                                             cout, terms, 0, st))
                 ptrs = (a_hi, a_lo, w_hi, w_lo)
-        ctx.save_for_backward(q, s, inds, kp, w, keep)
+        ctx.save_for_backward(q, s, inds, kp, w, keep)  # autograd's version check on w also guards its bf16 pair
         ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64, ld, npad, ptrs)
+        ctx.wkeep = None if fp32 else wkeep
         return out
 
     @staticmethod

@@ -175,6 +175,18 @@ int mvk_kpconv_deform_weighted_bwd(const float* q_pts, int nq, const float* s_pt
 int mvk_split_bf16(const float* src, int rows, int cols, int src_ld, void* hi, void* lo, int rows_pad,
                    int ld, mvk_stream_t stream);
 
+/* The same split for MANY matrices in one launch (all weight matrices of a model, once per optimiser
+ * step).  table_dev: device array of n_tensors descriptors ordered by first_chunk; tensor i owns the chunk
+ * range [first_chunk_i, first_chunk_i + ceil(rows_pad * dst_ld / 4096)) of the grid; dst_ld must be even and
+ * hi / lo 4-byte aligned. */
+typedef struct mvk_split_desc {
+    const float* src;
+    void* hi;
+    void* lo;
+    int rows, cols, src_ld, rows_pad, dst_ld, first_chunk;
+} mvk_split_desc;
+int mvk_split_bf16_multi(const mvk_split_desc* table_dev, int n_tensors, int total_chunks, mvk_stream_t stream);
+
 /* Tensor-core contraction (tcgen05 + TMA, fp32 accumulation in TMEM):
  *      D[m, n] (+)= sum_k A(m,k) * B(k,n)          for m < M, n < n_valid
  * Operands are bf16 hi/lo pairs; terms = 3 evaluates hi*hi + lo*hi + hi*lo (fp32-grade, ~2^-16

@@ -161,3 +161,57 @@ def test_softmax_cross_entropy_vs_torch(mvk):
     y = torch.full((10,), -1).cuda()
     out = mvk.softmax_cross_entropy(x, y)
     assert np.isnan(out.item())
+
+
+def test_weight_operand_pairs_follow_the_optimizer(mvk):
+    """The bf16 hi/lo pairs of the weights are refreshed once per optimiser step (one multi-tensor launch for
+    every registered parameter): after in-place updates the outputs must follow the NEW weights, for every
+    registered layer, and a backward through a graph whose weight changed in between must raise."""
+    import torch
+    from mvkpconv_b200 import _weights
+    torch.manual_seed(0)
+    dev = torch.device("cuda")
+    a = mvk.UnaryBlock(64, 48, True, 0.1).to(dev)
+    b = mvk.UnaryBlock(48, 40, False, 0.1).to(dev)
+    conv = mvk.KPConv(15, 3, 8, 24, 0.06, 0.15).to(dev)
+    pts = torch.rand(300, 3, device=dev) * 0.4
+    inds = mvk.batch_neighbors(pts, pts, torch.tensor([300], dtype=torch.int32, device=dev),
+                               torch.tensor([300], dtype=torch.int32, device=dev), 0.15).long()
+    x = torch.randn(300, 64, device=dev)
+    xc = torch.randn(300, 8, device=dev)
+
+    def run(contraction):
+        for m in (a, b, conv):
+            for mm in m.modules():
+                if hasattr(mm, "contraction"):
+                    mm.contraction = contraction
+        a.eval(); b.eval()
+        return b(a(x)).detach().clone(), conv(pts, pts, inds, xc).detach().clone()
+
+    for step in range(3):
+        got = run("bf16x3")
+        ref = run("fp32")                     # fp32 path reads the parameters directly
+        for g, r in zip(got, ref):
+            assert float((g - r).abs().max()) <= 1e-4 * float(r.abs().max())
+        params = [p for p in list(a.parameters()) + list(b.parameters()) + list(conv.parameters()) if p.requires_grad]
+        if step == 0:
+            with torch.no_grad():             # plain in-place updates: the version counters move
+                for p in params:
+                    p.add_(0.5 * torch.randn_like(p))
+        else:                                 # a FUSED optimiser does not move them: the step post-hook must
+            opt = torch.optim.SGD(params, lr=0.5, fused=True)
+            for p in params:
+                p.grad = torch.randn_like(p)
+            before = [p._version for p in params]
+            opt.step()
+            if [p._version for p in params] == before:
+                pass                          # (documented torch behaviour this guard exists for)
+    t = _weights._table(dev)
+    assert len(t.order) >= 3 and not t.dirty  # the second and third refresh went through the multi-tensor table
+    # stale pair guard
+    a.train()
+    y = a(x.requires_grad_(True)).sum()
+    with torch.no_grad():
+        a.mlp.weight.mul_(2.0)
+    with pytest.raises(RuntimeError):
+        y.backward()
