@@ -263,39 +263,51 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int rows, i
 }
 
 // out = leaky(y * scale + shift [+ residual]) ; optional bf16 hi/lo copy for a following contraction.
+// Thread (tx, ty) owns one column vector for the whole kernel (its scale / shift live in registers) and
+// walks the CTA's row slab four rows at a time (up to eight independent 16-byte loads in flight).
 template <int VEC>
 __global__ void __launch_bounds__(TB)
 scale_shift_act_kernel(const float* __restrict__ y, int rows, int cols, int ld, const float* __restrict__ scale,
                        const float* __restrict__ shift, const float* __restrict__ residual, int ldr, float slope,
                        float* __restrict__ out, int ldo, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                       int ldh) {
+                       int ldh, int rows_per_cta) {
     pdl_enter();
-    const int cv = cols / VEC;
-    const size_t total = (size_t)rows * cv;
-    for (size_t t = (size_t)blockIdx.x * TB + threadIdx.x; t < total; t += (size_t)gridDim.x * TB) {
-        const int r = (int)(t / cv), c = (int)(t % cv) * VEC;
-        float v[VEC], sc[VEC], sh[VEC];
-        loadv<VEC>(y + (size_t)r * ld + c, v);
-        if (scale) {
-            loadv<VEC>(scale + c, sc);
-            loadv<VEC>(shift + c, sh);
+    const Map2D m = make_map2d(cols, VEC);
+    const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
+    const int cvi = blockIdx.y * m.cpb + tx;
+    if (ty >= m.rpi || cvi >= m.cv) return;
+    const int c = cvi * VEC;
+    float sc[VEC], sh[VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; e++) v[e] = fmaf(v[e], sc[e], sh[e]);
-        } else if (shift) {
-            loadv<VEC>(shift + c, sh);
+    for (int e = 0; e < VEC; e++) {
+        sc[e] = scale ? scale[c + e] : 1.f;
+        sh[e] = shift ? shift[c + e] : 0.f;
+    }
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int rb = r0 + ty; rb < r1; rb += 4 * m.rpi) {
+        float v[4][VEC], rs[4][VEC];
 #pragma unroll
-            for (int e = 0; e < VEC; e++) v[e] += sh[e];
+        for (int u = 0; u < 4; u++) {
+            const int r = rb + u * m.rpi;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) v[u][e] = rs[u][e] = 0.f;
+            if (r < r1) {
+                loadv<VEC>(y + (size_t)r * ld + c, v[u]);
+                if (residual) loadv<VEC>(residual + (size_t)r * ldr + c, rs[u]);
+            }
         }
-        if (residual) {
-            float rs[VEC];
-            loadv<VEC>(residual + (size_t)r * ldr + c, rs);
 #pragma unroll
-            for (int e = 0; e < VEC; e++) v[e] += rs[e];
+        for (int u = 0; u < 4; u++) {
+            const int r = rb + u * m.rpi;
+            if (r >= r1) break;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const float t = fmaf(v[u][e], sc[e], sh[e]) + rs[u][e];
+                v[u][e] = t > 0.f ? t : t * slope;
+            }
+            if (out) storev<VEC>(out + (size_t)r * ldo + c, v[u]);
+            if (hi) store_hilo<VEC>(hi + (size_t)r * ldh + c, lo + (size_t)r * ldh + c, v[u]);
         }
-#pragma unroll
-        for (int e = 0; e < VEC; e++) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
-        if (out) storev<VEC>(out + (size_t)r * ldo + c, v);
-        if (hi) store_hilo<VEC>(hi + (size_t)r * ldh + c, lo + (size_t)r * ldh + c, v);
     }
 }
 
@@ -360,6 +372,7 @@ act_bwd_reduce_kernel(const float* __restrict__ dz, int lddz, const float* __res
 // dy = scale * (d - sum_d / rows - xhat * sum_dxhat / rows)   (batch norm, training)
 // dy = scale * d                                              (eval / no batch norm: scale may be NULL = 1)
 // d_res = d (gradient of the residual input), optional.
+// Same thread mapping as scale_shift_act_kernel: the six per-column constants stay in registers.
 template <int VEC>
 __global__ void __launch_bounds__(TB)
 act_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __restrict__ y, int rows, int cols, int ld,
@@ -368,42 +381,60 @@ act_bwd_apply_kernel(const float* __restrict__ dz, int lddz, const float* __rest
                      const float* __restrict__ invstd, float slope, const double* __restrict__ sums, int batch_stats,
                      float* __restrict__ dy, int lddy, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                      int ldh, float* __restrict__ dres, int lddres, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
+                     float* __restrict__ dbeta, int rows_per_cta) {
     pdl_enter();
-    if (blockIdx.x == 0 && sums) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && sums) {
         for (int c = threadIdx.x; c < cols; c += TB) {
             if (dbeta) dbeta[c] = (float)sums[c];
             if (dgamma) dgamma[c] = (float)sums[cols + c];
         }
     }
-    const int cv = cols / VEC;
-    const size_t total = (size_t)rows * cv;
+    const Map2D m = make_map2d(cols, VEC);
+    const int tx = threadIdx.x % m.cpb, ty = threadIdx.x / m.cpb;
+    const int cvi = blockIdx.y * m.cpb + tx;
+    if (ty >= m.rpi || cvi >= m.cv) return;
+    const int c = cvi * VEC;
     const float inv_rows = 1.f / (float)rows;
-    for (size_t t = (size_t)blockIdx.x * TB + threadIdx.x; t < total; t += (size_t)gridDim.x * TB) {
-        const int r = (int)(t / cv), c = (int)(t % cv) * VEC;
-        float v[VEC], g[VEC], rs[VEC], o[VEC], d[VEC];
-        loadv<VEC>(y + (size_t)r * ld + c, v);
-        loadv<VEC>(dz + (size_t)r * lddz + c, g);
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC], s0[VEC], s1[VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; e++) rs[e] = 0.f;
-        if (residual) loadv<VEC>(residual + (size_t)r * ldr + c, rs);
+    for (int e = 0; e < VEC; e++) {
+        sc[e] = scale ? scale[c + e] : 1.f;
+        sh[e] = shift ? shift[c + e] : 0.f;
+        mu[e] = batch_stats ? mean[c + e] : 0.f;
+        is[e] = batch_stats ? invstd[c + e] : 0.f;
+        s0[e] = batch_stats ? (float)sums[c + e] * inv_rows : 0.f;
+        s1[e] = batch_stats ? (float)sums[cols + c + e] * inv_rows : 0.f;
+    }
+    const int r0 = blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+    for (int rb = r0 + ty; rb < r1; rb += 2 * m.rpi) {
+        float v[2][VEC], g[2][VEC], rs[2][VEC];
 #pragma unroll
-        for (int e = 0; e < VEC; e++) {
-            const float sc = scale ? scale[c + e] : 1.f;
-            const float sh = shift ? shift[c + e] : 0.f;
-            const float pre = fmaf(v[e], sc, sh) + rs[e];
-            d[e] = pre > 0.f ? g[e] : g[e] * slope;
-            if (batch_stats) {
-                const float xh = (v[e] - mean[c + e]) * invstd[c + e];
-                const float s0 = (float)sums[c + e] * inv_rows, s1 = (float)sums[cols + c + e] * inv_rows;
-                o[e] = sc * (d[e] - s0 - xh * s1);
-            } else {
-                o[e] = sc * d[e];
+        for (int u = 0; u < 2; u++) {
+            const int r = rb + u * m.rpi;
+#pragma unroll
+            for (int e = 0; e < VEC; e++) v[u][e] = g[u][e] = rs[u][e] = 0.f;
+            if (r < r1) {
+                loadv<VEC>(y + (size_t)r * ld + c, v[u]);
+                loadv<VEC>(dz + (size_t)r * lddz + c, g[u]);
+                if (residual) loadv<VEC>(residual + (size_t)r * ldr + c, rs[u]);
             }
         }
-        if (dy) storev<VEC>(dy + (size_t)r * lddy + c, o);
-        if (hi) store_hilo<VEC>(hi + (size_t)r * ldh + c, lo + (size_t)r * ldh + c, o);
-        if (dres) storev<VEC>(dres + (size_t)r * lddres + c, d);
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int r = rb + u * m.rpi;
+            if (r >= r1) break;
+            float o[VEC], d[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; e++) {
+                const float pre = fmaf(v[u][e], sc[e], sh[e]) + rs[u][e];
+                d[e] = pre > 0.f ? g[u][e] : g[u][e] * slope;
+                // batch_stats == 0: s0 = s1 = 0, so this is sc * d
+                o[e] = sc[e] * (d[e] - s0[e] - (v[u][e] - mu[e]) * is[e] * s1[e]);
+            }
+            if (dy) storev<VEC>(dy + (size_t)r * lddy + c, o);
+            if (hi) store_hilo<VEC>(hi + (size_t)r * ldh + c, lo + (size_t)r * ldh + c, o);
+            if (dres) storev<VEC>(dres + (size_t)r * lddres + c, d);
+        }
     }
 }
 
@@ -431,6 +462,20 @@ inline int slab_rows(int rows, int cols, int vec, dim3* grid, int* cluster) {
     *cluster = gx >= CLUSTER ? CLUSTER : 1;
     gx = (gx + *cluster - 1) / *cluster * *cluster;  // CTAs past the last slab see an empty row range
     *grid = dim3(gx, ncg, 1);
+    return rpc;
+}
+// Row slabs for the streaming kernels with the (tx, ty) mapping: ~8 CTAs per SM, slabs a multiple of the
+// rows one CTA covers per trip.
+inline int stream_rows(int rows, int cols, int vec, int unroll, dim3* grid) {
+    Map2D m = make_map2d(cols, vec);
+    const int ncg = (m.cv + m.cpb - 1) / m.cpb;
+    int target = num_sms() * 8 / ncg;
+    if (target < 1) target = 1;
+    const int trip = m.rpi * unroll;
+    int rpc = (rows + target - 1) / target;
+    rpc = (rpc + trip - 1) / trip * trip;
+    if (rpc < trip) rpc = trip;
+    *grid = dim3((rows + rpc - 1) / rpc, ncg, 1);
     return rpc;
 }
 inline int ew_grid(size_t total) {
@@ -497,15 +542,14 @@ int mvk_scale_shift_act(const float* y, int rows, int cols, int ld, const float*
         return MVK_ERR_INVALID_ARG;
     if (rows == 0) return MVK_OK;
     const int vec = vec_for(cols, ld, residual ? ldr : 4, out ? ldo : 4, out_hi ? ldh : 4);
-    const int grid = ew_grid((size_t)rows * (cols / vec));
+    dim3 grid;
+    const int rpc = stream_rows(rows, cols, vec, 4, &grid);
     if (vec == 4)
-        launch_pdl(scale_shift_act_kernel<4>, dim3(grid), dim3(TB), 0, (cudaStream_t)stream, 1, y, rows, cols, ld, scale, shift, residual, ldr,
-                                                                        slope, out, ldo, (__nv_bfloat16*)out_hi,
-                                                                        (__nv_bfloat16*)out_lo, ldh);
+        launch_pdl(scale_shift_act_kernel<4>, grid, dim3(TB), 0, (cudaStream_t)stream, 1, y, rows, cols, ld, scale, shift,
+                   residual, ldr, slope, out, ldo, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ldh, rpc);
     else
-        launch_pdl(scale_shift_act_kernel<1>, dim3(grid), dim3(TB), 0, (cudaStream_t)stream, 1, y, rows, cols, ld, scale, shift, residual, ldr,
-                                                                        slope, out, ldo, (__nv_bfloat16*)out_hi,
-                                                                        (__nv_bfloat16*)out_lo, ldh);
+        launch_pdl(scale_shift_act_kernel<1>, grid, dim3(TB), 0, (cudaStream_t)stream, 1, y, rows, cols, ld, scale, shift,
+                   residual, ldr, slope, out, ldo, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo, ldh, rpc);
     MVK_LAUNCHED("scale_shift_act");
     return MVK_OK;
 }
@@ -542,17 +586,16 @@ int mvk_act_bwd_apply(const float* dz, int lddz, const float* y, int rows, int c
     if (rows > 0 && (dy || dy_hi || dres)) {
         int vec = vec_for(cols, ld, lddz, residual ? ldr : 4, dy ? lddy : 4);
         if (vec == 4 && ((dy_hi && ldh % 4 != 0) || (dres && lddres % 4 != 0))) vec = 1;
-        const int grid = ew_grid((size_t)rows * (cols / vec));
+        dim3 grid;
+        const int rpc = stream_rows(rows, cols, vec, 2, &grid);
         if (vec == 4)
-            launch_pdl(act_bwd_apply_kernel<4>, dim3(grid), dim3(TB), 0, st, 1, dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
-                                                         invstd, slope, sums, batch_stats, dy, lddy,
-                                                         (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres,
-                                                         dgamma, dbeta);
+            launch_pdl(act_bwd_apply_kernel<4>, grid, dim3(TB), 0, st, 1, dz, lddz, y, rows, cols, ld, scale, shift, residual,
+                       ldr, mean, invstd, slope, sums, batch_stats, dy, lddy, (__nv_bfloat16*)dy_hi,
+                       (__nv_bfloat16*)dy_lo, ldh, dres, lddres, dgamma, dbeta, rpc);
         else
-            launch_pdl(act_bwd_apply_kernel<1>, dim3(grid), dim3(TB), 0, st, 1, dz, lddz, y, rows, cols, ld, scale, shift, residual, ldr, mean,
-                                                         invstd, slope, sums, batch_stats, dy, lddy,
-                                                         (__nv_bfloat16*)dy_hi, (__nv_bfloat16*)dy_lo, ldh, dres, lddres,
-                                                         dgamma, dbeta);
+            launch_pdl(act_bwd_apply_kernel<1>, grid, dim3(TB), 0, st, 1, dz, lddz, y, rows, cols, ld, scale, shift, residual,
+                       ldr, mean, invstd, slope, sums, batch_stats, dy, lddy, (__nv_bfloat16*)dy_hi,
+                       (__nv_bfloat16*)dy_lo, ldh, dres, lddres, dgamma, dbeta, rpc);
         MVK_LAUNCHED("act_bwd_apply");
     } else if ((dgamma || dbeta) && sums) {
         bn_param_grads_kernel<<<(cols + 255) / 256, 256, 0, st>>>(sums, cols, dgamma, dbeta);

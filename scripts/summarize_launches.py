@@ -9,7 +9,10 @@ rows = [r for r in csv.DictReader(lines) if r['ID'] != '']
 names = [r['Kernel Name'] for r in rows]
 dur = [float(r['Metric Value']) / 1e3 for r in rows]
 ks = [i for i, n in enumerate(names) if 'k_starts' in n]
-a, b = ks[-13], len(rows)  # 13 neighbour calls per step; the step starts with the first one
+# 13 neighbour calls per pyramid.  With the side-stream prefetcher an iteration is [training of batch i,
+# pyramid of batch i+1]; ncu serialises the streams, so one full cycle = from the first launch of the
+# second-to-last pyramid up to the first launch of the last one (pyramid + training pass + optimiser).
+a, b = ks[-26], ks[-13]
 tot = sum(dur[a:b])
 def short(n):
     n = n.replace('void ', '').replace('mvk::<unnamed>::', 'mvk::')
@@ -22,7 +25,7 @@ mv = sum(v[1] for k, v in agg.items() if k.startswith('mvk'))
 mvn = sum(v[0] for k, v in agg.items() if k.startswith('mvk'))
 out = [f"# Round 1, capture {tag}: ncu launch list of the bench command\n",
        f"Command (`scripts/gpu_profile.sh {tag} list`): `ncu --metrics gpu__time_duration.sum --clock-control none -c 12000 --csv "
-       f"python bench.py --steps 1 --warmup 3 --quick`; the table covers the LAST step (launches {a}..{b} of `{tag}_launches.csv`).  "
+       f"python bench.py --steps 1 --warmup 3 --quick`; the table covers one full step cycle (launches {a}..{b} of `{tag}_launches.csv`).  "
        "Per-launch times are cold-cache and serialised: compare SHARES, not absolutes.\n",
        f"{b - a} launches in the step, {tot / 1e3:.1f} ms of kernel time; libmvk kernels: {mvn} launches, {mv / 1e3:.1f} ms "
        f"({100 * mv / tot:.0f}%); library kernels (torch: loss, cat, optimizer, fills, gradient accumulation): {(tot - mv) / 1e3:.1f} ms.\n",
