@@ -34,6 +34,8 @@ def _workspace(nbytes, device, kind="subsample"):
 
 def _dev(x, dtype, device=None):
     if isinstance(x, torch.Tensor):
+        if x.dtype is dtype and x.is_cuda and x.is_contiguous():
+            return x  # the common case inside the pyramid: nothing to convert
         if not x.is_cuda:
             x = x.cuda(device) if device is not None else x.cuda()
         return x.to(dtype).contiguous()
