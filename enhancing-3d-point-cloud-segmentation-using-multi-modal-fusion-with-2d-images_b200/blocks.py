@@ -238,6 +238,12 @@ class _LinearBNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz):
+        dx, dw, dgamma, dbeta, dres = _LinearBNAct._backward(ctx, dz, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                                            ctx.needs_input_grad[4])
+        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
+
+    @staticmethod
+    def _backward(ctx, dz, need_x, need_w, need_res):
         L = _lib.lib()
         keep, xkeep, res, xf, w, _bias = ctx.saved_tensors
         rows, cin, cout, use_bn, training, slope, has_g, has_b, contraction, ldx, ptrs, _wkeep = ctx.cfg
@@ -245,7 +251,6 @@ class _LinearBNAct(torch.autograd.Function):
         g, ldg = _rows_f32(dz)
         dev = g.device
         st = stream_ptr()
-        need_x, need_w, need_res = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
         batch_stats = 1 if (use_bn and training) else 0
         dx = dw = None
         with _lib.on_device(dev):
@@ -293,7 +298,72 @@ class _LinearBNAct(torch.autograd.Function):
                         # dW = dy^T x : both operands stored [K = rows, *] with the M / N index contiguous
                         check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 1, ldh, x_hi, x_lo, 1, ldx, cout, cin, rows, dw.data_ptr(),
                                                 cin, cin, terms, split, st))
-        return dx, dw, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
+        return dx, dw, dgamma, dbeta, dres
+
+
+class _PreSplit:
+    """Stands in for an activation tensor whose fp32 form is never materialised: only its bf16 hi/lo
+    operand pair exists (written by a fused producer).  _LinearBNAct.forward only asks an input for its
+    shape / device / cached pair on the tensor-core paths."""
+    dtype = torch.float32
+    is_cuda = True
+    _version = 0
+
+    def __init__(self, rows, cols, device, keep, hi, lo, ld):
+        self.shape, self.device = (rows, cols), device
+        self._mvk_hilo = _HiLo(keep, hi, lo, rows, ld, 0)
+
+    def is_contiguous(self):
+        return True
+
+
+class _UpCatLinearBNAct(torch.autograd.Function):
+    """z = leaky(bn(cat([closest_pool(x_coarse, inds), skip], 1) W^T)): the decoder step of KPFCNN
+    (architectures.py:300-306 + blocks.py:493-498) with the concatenation fused into the operand split.
+    Argument positions 0 / 1 / 4 mirror _LinearBNAct (x, weight, residual)."""
+
+    @staticmethod
+    def forward(ctx, x_coarse, weight, gamma, beta, skip, rm, rv, use_bn, training, momentum, eps, slope, contraction,
+                nbt, emit_hilo, inds):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if contraction == "fp32":
+            raise RuntimeError("the fused decoder step needs a tensor-core contraction ('bf16x3' or 'bf16')")
+        xc, sk = _f32c(x_coarse), _f32c(skip)
+        ii, is64 = _kp._idx(inds if inds.dim() == 2 else inds.reshape(-1, 1))
+        ns, c1 = xc.shape
+        nq, c2 = sk.shape
+        if ii.shape[0] != nq or c1 % 4 or c2 % 4 or (c1 + c2) % 8:
+            raise RuntimeError("upsample+concat: channel counts must be multiples of 4 (sum: of 8)")
+        dev = xc.device
+        ldh = c1 + c2
+        with _lib.on_device(dev):
+            ukeep, (u_hi, u_lo) = _carve(dev, 2 * nq * ldh, 2 * nq * ldh)
+            check(L.mvk_upsample_concat_split(xc.data_ptr(), ns, c1, ii.data_ptr(), is64, nq, ii.shape[1], sk.data_ptr(),
+                                              c2, c2, u_hi, u_lo, ldh, stream_ptr()))
+        virt = _PreSplit(nq, ldh, dev, ukeep, u_hi, u_lo, ldh)
+        z = _LinearBNAct.forward(ctx, virt, weight, gamma, beta, None, rm, rv, use_bn, training, momentum, eps, slope,
+                                 contraction, nbt, emit_hilo)
+        ctx.up = (ii, is64, ns, c1, c2)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        L = _lib.lib()
+        need_c, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[4]
+        dx, dw, dgamma, dbeta, _ = _LinearBNAct._backward(ctx, dz, need_c or need_s, ctx.needs_input_grad[1], False)
+        ii, is64, ns, c1, c2 = ctx.up
+        dcoarse = dskip = None
+        if dx is not None:
+            nq = dx.shape[0]
+            if need_s:
+                dskip = dx[:, c1:]  # a view: consumers take the row pitch (or copy)
+            if need_c:
+                dcoarse = torch.zeros((ns, c1), dtype=torch.float32, device=dx.device)
+                with _lib.on_device(dx.device):
+                    check(L.mvk_pool_bwd(dx.data_ptr(), c1 + c2, nq, c1, None, ii.data_ptr(), is64, ii.shape[1], 1, ns,
+                                         dcoarse.data_ptr(), stream_ptr()))
+        return dcoarse, dw, dgamma, dbeta, dskip, None, None, None, None, None, None, None, None, None, None, None
 
 
 # -------------------------------------------------------------------------------------------------
@@ -364,6 +434,16 @@ class UnaryBlock(nn.Module):
         use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(self.batch_norm)
         return _LinearBNAct.apply(x, self.mlp.weight, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps,
                                   float(slope), self.contraction, _nbt(mod, x.shape[0]), emit_hilo)
+
+    def forward_upsampled(self, x_coarse, up_inds, skip, emit_hilo=False):
+        """``self(torch.cat([closest_pool(x_coarse, up_inds), skip], dim=1))`` -- the decoder step of KPFCNN
+        (architectures.py:300-306) -- without materialising the upsampled or the concatenated tensor."""
+        if self.contraction == "fp32" or x_coarse.shape[1] % 4 or skip.shape[1] % 4 or self.in_dim % 8:
+            return self.forward(torch.cat([_kp.closest_pool(x_coarse, up_inds), skip], dim=1), emit_hilo=emit_hilo)
+        slope = 1.0 if self.no_relu else 0.1
+        use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(self.batch_norm)
+        return _UpCatLinearBNAct.apply(x_coarse, self.mlp.weight, gamma, beta, skip, rm, rv, use_bn, training, momentum,
+                                       eps, float(slope), self.contraction, _nbt(mod, skip.shape[0]), emit_hilo, up_inds)
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(self.in_dim, self.out_dim,

@@ -339,6 +339,38 @@ split_bf16_multi(const mvk_split_desc* __restrict__ table, int n) {
     }
 }
 
+// Decoder entry of KPFCNN (architectures.py:300-306): x = cat([closest_pool(x_coarse, up_inds), skip], dim=1)
+// feeding a unary block.  The concatenated row only ever exists as the bf16 hi/lo operand of that block's
+// Linear: row r = [x_coarse[inds[r, 0]] (zero for the shadow index), skip[r]].  One float4 per thread and trip.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+upcat_split_kernel(const float* __restrict__ xc, int ns, int c1, const IdxT* __restrict__ inds, int h,
+                   const float* __restrict__ skip, int lds, int c2, int nq, __nv_bfloat16* __restrict__ hi,
+                   __nv_bfloat16* __restrict__ lo, int ldh) {
+    pdl_enter();
+    const int cv = (c1 + c2) / 4, cv1 = c1 / 4;
+    const size_t total = (size_t)nq * cv;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cv), c = (int)(t % cv);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < cv1) {
+            const long long j = (long long)inds[(size_t)r * h];
+            if (j >= 0 && j < ns) v = *(const float4*)(xc + (size_t)j * c1 + 4 * c);
+        } else {
+            v = *(const float4*)(skip + (size_t)r * lds + 4 * (c - cv1));
+        }
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y);
+        __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
+        uint2 ph, pl;
+        ph.x = *(unsigned int*)&h0; ph.y = *(unsigned int*)&h1;
+        pl.x = *(unsigned int*)&l0; pl.y = *(unsigned int*)&l1;
+        *(uint2*)(hi + (size_t)r * ldh + 4 * c) = ph;
+        *(uint2*)(lo + (size_t)r * ldh + 4 * c) = pl;
+    }
+}
+
 // mode 0: max over neighbours with a ZERO shadow row (blocks.py:93-110); mode 1: first column.
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
@@ -1007,6 +1039,26 @@ int mvk_split_bf16_multi(const mvk_split_desc* table_dev, int n_tensors, int tot
     if (!table_dev || n_tensors < 1 || total_chunks < 1) return MVK_ERR_INVALID_ARG;
     launch_pdl(split_bf16_multi, dim3(total_chunks), dim3(256), 0, (cudaStream_t)stream, 1, table_dev, n_tensors);
     MVK_LAUNCHED("split_bf16_multi");
+    return MVK_OK;
+}
+
+int mvk_upsample_concat_split(const float* x_coarse, int ns, int c1, const void* inds, int idx_is_i64, int nq, int h,
+                              const float* skip, int lds, int c2, void* hi, void* lo, int ldh, mvk_stream_t stream) {
+    if (!x_coarse || !inds || !skip || !hi || !lo || ns < 0 || nq < 0 || h < 1 || c1 < 4 || c2 < 4 || (c1 % 4) != 0 ||
+        (c2 % 4) != 0 || lds < c2 || (lds % 4) != 0 || ldh < c1 + c2 || (ldh % 4) != 0 ||
+        ((((size_t)x_coarse) | ((size_t)skip)) & 15) != 0 || ((((size_t)hi) | ((size_t)lo)) & 7) != 0)
+        return MVK_ERR_INVALID_ARG;
+    if (nq == 0) return MVK_OK;
+    const size_t nv = (size_t)nq * ((c1 + c2) / 4);
+    size_t nb = (nv + 255) / 256, mb = (size_t)num_sms() * 16;
+    const dim3 grid((unsigned)(nb < mb ? nb : mb));
+    if (idx_is_i64)
+        launch_pdl(upcat_split_kernel<long long>, grid, dim3(256), 0, (cudaStream_t)stream, 1, x_coarse, ns, c1,
+                   (const long long*)inds, h, skip, lds, c2, nq, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldh);
+    else
+        launch_pdl(upcat_split_kernel<int>, grid, dim3(256), 0, (cudaStream_t)stream, 1, x_coarse, ns, c1,
+                   (const int*)inds, h, skip, lds, c2, nq, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldh);
+    MVK_LAUNCHED("upcat_split_kernel");
     return MVK_OK;
 }
 

@@ -204,10 +204,23 @@ class KPFCNN(nn.Module):
             if i in self.encoder_skips:
                 skips.append(x)
             x = op(x, batch)
-        for j, op in enumerate(self.decoder_blocks):
+        j, blocks = 0, self.decoder_blocks
+        while j < len(blocks):
+            op = blocks[j]
+            # product path: nearest upsampling + skip concatenation + unary block as one fused step
+            if (self._product_ops and isinstance(op, NearestUpsampleBlock) and j + 1 < len(blocks) and
+                    (j + 1) in self.decoder_concats and hasattr(blocks[j + 1], "forward_upsampled")):
+                # the last decoder block feeds the head's Linear: it emits the bf16 pair of its output itself
+                x = blocks[j + 1].forward_upsampled(x, batch.upsamples[op.layer_ind - 1], skips.pop(),
+                                                    emit_hilo=(j + 2 == len(blocks)))
+                j += 2
+                continue
             if j in self.decoder_concats:
                 x = torch.cat([x, skips.pop()], dim=1)
             x = op(x, batch)
+            j += 1
+        if self._product_ops:
+            return self.head_softmax(self.head_mlp(x, batch, emit_hilo=True), batch)
         return self.head_softmax(self.head_mlp(x, batch), batch)
 
     def loss(self, outputs, labels):

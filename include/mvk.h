@@ -271,6 +271,14 @@ int mvk_softmax_xent_bwd(const float* logits, int ld, const long long* labels, i
                          long long ignore_index, const float* lse, const unsigned int* count, const float* upstream,
                          float* grad, int ldg, mvk_stream_t stream);
 
+/* Decoder entry (architectures.py:300-306): cat([closest_pool(x_coarse, inds), skip], dim=1) emitted directly as the
+ * bf16 hi/lo operand [nq, ldh] of the following unary block's Linear (the fp32 concatenation is never
+ * materialised).  inds [nq, h]: only column 0 is used; index ns (shadow) gathers zeros.  c1, c2, lds, ldh
+ * multiples of 4. */
+int mvk_upsample_concat_split(const float* x_coarse, int ns, int c1, const void* inds, int idx_is_i64, int nq, int h,
+                              const float* skip, int lds, int c2, void* hi_bf16, void* lo_bf16, int ldh,
+                              mvk_stream_t stream);
+
 /* Gather pools on the neighbour matrices (blocks.py:79-110): mode 0 = max_pool (zero-padded
  * shadow row!), 1 = closest_pool (first column).  arg_out [nq, c] i32 (max_pool only) records the
  * winning support row for the backward.  Backward: grad_x[arg] += grad_out. */

@@ -215,3 +215,34 @@ def test_weight_operand_pairs_follow_the_optimizer(mvk):
         a.mlp.weight.mul_(2.0)
     with pytest.raises(RuntimeError):
         y.backward()
+
+
+def test_fused_decoder_step_matches_unfused(mvk):
+    """UnaryBlock.forward_upsampled == unary(cat([closest_pool(x_coarse, up), skip], 1)) (architectures.py:300-306):
+    outputs and all gradients (coarse features, skip features, weight, gamma, beta), incl. shadow indices."""
+    import torch
+    torch.manual_seed(1)
+    dev = torch.device("cuda")
+    ns, nq, c1, c2, cout = 700, 2500, 64, 32, 48
+    blk = mvk.UnaryBlock(c1 + c2, cout, True, 0.1).to(dev)
+    up = torch.randint(0, ns + 1, (nq, 5), device=dev)   # ns = shadow index -> zero row
+    up[::7, 0] = ns
+    xc0 = torch.randn(ns, c1, device=dev)
+    sk0 = torch.randn(nq, c2, device=dev)
+    gz = torch.randn(nq, cout, device=dev)
+    res = {}
+    for mode in ("fused", "plain"):
+        blk.zero_grad(set_to_none=True)
+        xc, sk = xc0.clone().requires_grad_(True), sk0.clone().requires_grad_(True)
+        if mode == "fused":
+            z = blk.forward_upsampled(xc, up, sk)
+        else:
+            z = blk(torch.cat([mvk.closest_pool(xc, up), sk], dim=1))
+        (z * gz).sum().backward()
+        res[mode] = [z.detach(), xc.grad, sk.grad, blk.mlp.weight.grad.clone(), blk.batch_norm.batch_norm.weight.grad.clone(),
+                     blk.batch_norm.batch_norm.bias.grad.clone()]
+    for a, b in zip(res["fused"], res["plain"]):
+        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-7
+    blk.contraction = "fp32"   # falls back to the unfused sequence
+    z = blk.forward_upsampled(xc0, up, sk0)
+    assert float((z.detach() - res["plain"][0]).abs().max()) <= 1e-4 * float(res["plain"][0].abs().max())
