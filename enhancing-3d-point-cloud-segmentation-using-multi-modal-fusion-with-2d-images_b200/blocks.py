@@ -121,12 +121,15 @@ def _norm_forward(L, y_ptr, ld, rows, cols, use_bn, training, gamma, beta, rm, r
     return sc, sh, mu, isd
 
 
+_GRAD_HILO = os.environ.get("MVK_GRAD_HILO", "1") != "0"  # development switch (A/B timing)
+
+
 class _BNAct(torch.autograd.Function):
     """z = leaky(bn(y) [+ residual]); blocks.py:446-460 + the activation / residual that follows."""
 
     @staticmethod
     def forward(ctx, y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, slope, nbt=None,
-                emit_hilo=False):
+                emit_hilo=False, grad_hilo=False):
         _lib.require_cuda()
         L = _lib.lib()
         if not y.is_cuda:
@@ -147,6 +150,7 @@ class _BNAct(torch.autograd.Function):
                                         cols, hi, lo, cols, st))
         ctx.save_for_backward(yf, keep, res, beta if not use_bn else None)
         ctx.cfg = (rows, cols, use_bn, training, slope, gamma is not None, beta is not None, (sc, sh, mu, isd))
+        ctx.grad_hilo = bool(grad_hilo) and cols % 8 == 0 and _GRAD_HILO
         if emit:
             _attach_hilo(z, keep, hi, lo, rows, cols)
         return z
@@ -170,10 +174,14 @@ class _BNAct(torch.autograd.Function):
             dres = torch.empty_like(yf) if (need_res and res is not None) else None
             dgamma = torch.empty(cols, dtype=torch.float32, device=dev) if has_g else None
             dbeta = torch.empty(cols, dtype=torch.float32, device=dev) if has_b else None
+            # y came out of a KPConv: its backward contracts dy on the tensor cores, so the pair is written here
+            gkeep, (g_hi, g_lo) = _carve(dev, *([2 * rows * cols] * 2 if (ctx.grad_hilo and need_y) else [0, 0]))
             check(L.mvk_act_bwd_apply(g.data_ptr(), ldg, yf.data_ptr(), rows, cols, cols, sc, sh, ptr(res), cols, mu, isd,
-                                      slope, sums, batch_stats, ptr(dy), cols, None, None, 0, ptr(dres), cols,
+                                      slope, sums, batch_stats, ptr(dy), cols, g_hi, g_lo, cols, ptr(dres), cols,
                                       ptr(dgamma), ptr(dbeta), st))
-        return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
+            if g_hi is not None:
+                _attach_hilo(dy, gkeep, g_hi, g_lo, rows, cols)
+        return dy, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
 
 
 class _LinearBNAct(torch.autograd.Function):
@@ -400,12 +408,13 @@ def _nbt(bn_module, rows):
     return None
 
 
-def bn_act(y, bn_block, slope=0.1, residual=None, emit_hilo=False):
+def bn_act(y, bn_block, slope=0.1, residual=None, emit_hilo=False, grad_hilo=False):
     """leaky_relu(bn_block(y) [+ residual], slope); slope = 1 disables the activation.
-    emit_hilo: also write the result as a bf16 hi/lo pair for a following UnaryBlock (same kernel)."""
+    emit_hilo: also write the result as a bf16 hi/lo pair for a following UnaryBlock (same kernel).
+    grad_hilo: y is a KPConv output -- the backward also writes the gradient w.r.t. y as a bf16 pair."""
     use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(bn_block)
     return _BNAct.apply(y, gamma, beta, residual, rm, rv, use_bn, training, momentum, eps, float(slope),
-                        _nbt(mod, y.shape[0]), emit_hilo)
+                        _nbt(mod, y.shape[0]), emit_hilo, grad_hilo)
 
 
 class UnaryBlock(nn.Module):

@@ -90,7 +90,7 @@ class SimpleBlock(nn.Module):
         q, s, inds = _geometry(self.block_name, self.layer_ind, batch)
         y = self.KPConv(q, s, inds, x)
         if self.bn_act is not None:  # the output feeds the next block's Linear layers: emit their operand format too
-            return self.bn_act(y, self.batch_norm, slope=0.1, emit_hilo=True)
+            return self.bn_act(y, self.batch_norm, slope=0.1, emit_hilo=True, grad_hilo=True)
         return self.leaky_relu(self.batch_norm(y))
 
 
@@ -120,7 +120,7 @@ class ResnetBottleneckBlock(nn.Module):
         y = self.KPConv(q, s, inds, x)
         shortcut = self.ops.max_pool(features, inds) if 'strided' in self.block_name else features
         if self.bn_act is not None:  # product path: fused bn + act, and bn + residual + act tail
-            x = self.bn_act(y, self.batch_norm_conv, slope=0.1, emit_hilo=True)
+            x = self.bn_act(y, self.batch_norm_conv, slope=0.1, emit_hilo=True, grad_hilo=True)
             return self.unary2(x, residual=self.unary_shortcut(shortcut), slope=0.1, emit_hilo=self.feeds_linear)
         x = self.leaky_relu(self.batch_norm_conv(y))
         x = self.unary2(x)

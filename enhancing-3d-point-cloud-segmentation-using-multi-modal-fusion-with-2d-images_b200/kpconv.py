@@ -142,8 +142,15 @@ class _KPConvFunction(torch.autograd.Function):
             else:
                 a_hi, a_lo, w_hi, w_lo = ptrs
                 terms = 3 if contraction == "bf16x3" else 1
-                bkeep, (dA, go_hi, go_lo) = _carve(dev, 4 * nq * ld if need_x else 0, 2 * nq * npad, 2 * nq * npad)
-                check(L.mvk_split_bf16(go.data_ptr(), nq, cout, cout, go_hi, go_lo, nq, npad, st))
+                cached = getattr(grad_out, "_mvk_hilo", None)  # written by the producer of grad_out (bn_act backward)
+                if cached is not None and (cached.version != grad_out._version or cached.rows != nq or cached.ld != npad):
+                    cached = None
+                nsplit = 0 if cached is not None else 2 * nq * npad
+                bkeep, (dA, go_hi, go_lo) = _carve(dev, 4 * nq * ld if need_x else 0, nsplit, nsplit)
+                if cached is not None:
+                    go_hi, go_lo, gokeep = cached.hi, cached.lo, cached.keep
+                else:
+                    check(L.mvk_split_bf16(go.data_ptr(), nq, cout, cout, go_hi, go_lo, nq, npad, st))
                 if need_w:
                     gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
                     if nq > 0:
