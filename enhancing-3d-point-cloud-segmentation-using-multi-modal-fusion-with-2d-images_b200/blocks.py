@@ -299,13 +299,14 @@ class _LinearBNAct(torch.autograd.Function):
                         check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 0, ldh, w_hi, w_lo, 1, ldx, rows, cin, cout, dx.data_ptr(),
                                                 cin, cin, terms, 0, st))
                 if need_w:
-                    dw = torch.zeros((cout, cin), dtype=torch.float32, device=dev)
                     if rows > 0:
-                        kb_total = (rows + 63) // 64
-                        split = _kp._split_k_for((cout + 127) // 128, (cin + 127) // 128 if cin > 64 else 1, kb_total)
-                        # dW = dy^T x : both operands stored [K = rows, *] with the M / N index contiguous
+                        # dW = dy^T x : both operands stored [K = rows, *] with the M / N index contiguous;
+                        # split_k = 0: the library splits the reduction over the SMs and zeroes dW itself
+                        dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
                         check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 1, ldh, x_hi, x_lo, 1, ldx, cout, cin, rows, dw.data_ptr(),
-                                                cin, cin, terms, split, st))
+                                                cin, cin, terms, 0, st))
+                    else:
+                        dw = torch.zeros((cout, cin), dtype=torch.float32, device=dev)
         return dx, dw, dgamma, dbeta, dres
 
 

@@ -509,7 +509,7 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int a_mn_major, int lda
         const int tiles = ((M + BM - 1) / BM) * ((n_valid + p.bn - 1) / p.bn);
         split_k = 1;
         if (tiles * 2 <= num_sms() && p.kb_total >= 8) {
-            split_k = num_sms() / tiles;
+            split_k = 2 * num_sms() / tiles;  // two work items per persistent CTA
             if (split_k > p.kb_total / 4) split_k = p.kb_total / 4;
             if (split_k < 1) split_k = 1;
         }

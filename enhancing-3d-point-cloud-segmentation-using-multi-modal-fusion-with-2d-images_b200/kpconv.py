@@ -152,13 +152,14 @@ class _KPConvFunction(torch.autograd.Function):
                 else:
                     check(L.mvk_split_bf16(go.data_ptr(), nq, cout, cout, go_hi, go_lo, nq, npad, st))
                 if need_w:
-                    gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
                     if nq > 0:
-                        kb_total = (nq + 63) // 64
-                        split = _split_k_for((kd + 127) // 128, (npad + 127) // 128, kb_total)
-                        # dW = A^T dOut, both operands MN-major, reduction over the points
+                        # dW = A^T dOut, both operands MN-major, reduction over the points; split_k = 0: the library
+                        # splits the reduction over the SMs and zeroes dW itself
+                        gw = torch.empty((K, cin, cout), dtype=torch.float32, device=dev)
                         check(L.mvk_gemm_bf16x3(a_hi, a_lo, 1, ld, go_hi, go_lo, 1, npad, kd, npad, nq, gw.data_ptr(), cout,
-                                                cout, terms, split, st))
+                                                cout, terms, 0, st))
+                    else:
+                        gw = torch.zeros((K, cin, cout), dtype=torch.float32, device=dev)
                 if need_x and nq > 0:
                     # dA = dOut W^T : A = dOut [nq, npad] K-major, B = W [ld, npad] K-major
                     check(L.mvk_gemm_bf16x3(go_hi, go_lo, 0, npad, w_hi, w_lo, 0, npad, nq, ld, npad, dA, ld, ld, terms,
