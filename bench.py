@@ -468,7 +468,7 @@ def cpu_reference(steps, warmup, seed=0, n_spheres=1):
         t2 = time.perf_counter()
         t_pyr += t1 - t0
         t_net += t2 - t1
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()
