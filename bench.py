@@ -154,6 +154,7 @@ def run_b200(args):
             for t in list(net.parameters()) + list(net.buffers()):
                 dist.broadcast(t, 0)
     grad_params = [p for p in net.parameters() if p.requires_grad]
+    averager = harness.OverlappedGradientAverager(net, split_level=3) if (world > 1 and args.allreduce == "overlap") else None
 
     def allreduce_grads():
         """Gradient averaging right after backward, without DDP's buckets and per-parameter hooks.
@@ -161,6 +162,9 @@ def run_b200(args):
         copy-back).  'flat': the tensors are packed into one buffer by a multi-tensor copy, one all-reduce
         (average) runs on it and the .grad are re-pointed at views of it -- measured no faster at 2 GPUs
         (13.5 vs 13.3 ms per step), kept for comparison."""
+        if averager is not None:
+            averager.finish()  # the deep levels' gradients have been in flight since the middle of backward
+            return
         ps = [p for p in grad_params if p.grad is not None]
         grads = [p.grad for p in ps]
         if args.allreduce == "flat":
@@ -526,7 +530,7 @@ def main():
     ap.add_argument("--contraction", default=os.environ.get("MVK_CONTRACTION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--allreduce", default="coalesced", choices=["coalesced", "flat", "ddp"],
+    ap.add_argument("--allreduce", default="coalesced", choices=["coalesced", "overlap", "flat", "ddp"],
                     help="N > 1: gradients packed into one buffer + ONE NCCL all-reduce (flat), a grouped all-reduce of the "
                          "per-parameter tensors (coalesced), or torch DDP buckets (ddp)")
     ap.add_argument("--detail", type=int, default=0, help="add the N most expensive (entry point, shape) rows")

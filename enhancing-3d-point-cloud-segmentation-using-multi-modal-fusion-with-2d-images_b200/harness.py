@@ -256,3 +256,71 @@ class KPFCNN(nn.Module):
         """Top-level KPConv modules (the offset convolutions nested inside deformable ones excluded)."""
         nested = {id(m.offset_conv) for m in self.modules() if getattr(m, "offset_conv", None) is not None}
         return [m for m in self.modules() if type(m).__name__.startswith("KPConv") and id(m) not in nested]
+
+
+class OverlappedGradientAverager:
+    """Gradient averaging over the ranks of a sphere-sharded job, overlapped with backward.
+
+    Backward produces the gradients of the decoder and of the deep encoder levels first -- the bulk of the
+    parameter bytes (level >= 3 holds ~90 % of the 24.4 M parameters of the baseline network) -- and spends
+    most of its time afterwards in the shallow, point-heavy levels.  A post-accumulate hook on the LAST
+    parameter of that early group starts its all-reduce asynchronously (NCCL's own stream), so the transfer
+    hides behind the rest of backward; ``finish()`` (call it after ``loss.backward()``) reduces whatever is
+    left, waits, and divides by the world size.  No per-parameter hooks, no buckets, no copies.
+
+        avg = OverlappedGradientAverager(net, split_level=3)     # once
+        loss.backward(); avg.finish()                            # every step
+    """
+
+    def __init__(self, net, split_level=3, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.coalesce = dist.get_backend(group) == "nccl"
+        late_ids, trigger = set(), None
+        for blk in net.encoder_blocks:
+            if getattr(blk, "layer_ind", 0) < split_level:
+                late_ids.update(id(p) for p in blk.parameters())
+        for blk in net.encoder_blocks:  # first block of the early group = the one whose backward runs last
+            if getattr(blk, "layer_ind", 0) >= split_level:
+                ps = [p for p in blk.parameters() if p.requires_grad]
+                trigger = ps[0] if ps else None
+                break
+        params = [p for p in net.parameters() if p.requires_grad]
+        self.early = [p for p in params if id(p) not in late_ids]
+        self.params = params
+        self._works, self._sent = [], set()
+        self._hook = trigger.register_post_accumulate_grad_hook(self._fire) if trigger is not None else None
+
+    def _reduce(self, tensors, async_op):
+        dist = self.dist
+        if not tensors:
+            return
+        if self.coalesce:
+            with dist._coalescing_manager(group=self.group, device=tensors[0].device, async_ops=async_op) as cm:
+                for t in tensors:
+                    dist.all_reduce(t, group=self.group)
+            if async_op:
+                self._works.append(cm)
+        else:
+            for t in tensors:
+                w = dist.all_reduce(t, group=self.group, async_op=async_op)
+                if async_op:
+                    self._works.append(w)
+
+    def _fire(self, _param):
+        if self._sent:  # a second backward before finish(): leave everything to finish()
+            return
+        ready = [p for p in self.early if p.grad is not None]
+        self._sent = {id(p) for p in ready}
+        self._reduce([p.grad for p in ready], async_op=True)
+
+    def finish(self):
+        rest = [p.grad for p in self.params if p.grad is not None and id(p) not in self._sent]
+        self._reduce(rest, async_op=False)
+        for w in self._works:
+            w.wait()
+        self._works, self._sent = [], set()
+        grads = [p.grad for p in self.params if p.grad is not None]
+        if grads:
+            torch._foreach_div_(grads, float(self.world))

@@ -73,15 +73,26 @@ def _grads(net):
     return torch.cat([p.grad.reshape(-1) for p in net.parameters() if p.grad is not None])
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, mode="ddp"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     net, batch = _build(rank)
-    ddp = torch.nn.parallel.DistributedDataParallel(net)
     opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9)
-    loss = net.loss(ddp(batch), batch.labels)
-    loss.backward()
+    if mode == "ddp":
+        ddp = torch.nn.parallel.DistributedDataParallel(net)
+        loss = net.loss(ddp(batch), batch.labels)
+        loss.backward()
+    else:  # the bench's own averaging: early group in flight during backward, the rest afterwards
+        from mvkpconv_b200 import harness
+        avg = harness.OverlappedGradientAverager(net, split_level=1)
+        assert 0 < len(avg.early) < len(avg.params)
+        for _ in range(2):  # the hook must re-arm for every step
+            opt.zero_grad(set_to_none=True)
+            loss = net.loss(net(batch), batch.labels)
+            loss.backward()
+            assert avg._sent, "the early group was not sent from inside backward"
+            avg.finish()
     g = _grads(net)
     opt.step()
     w = torch.cat([p.detach().reshape(-1) for p in net.parameters()])
@@ -90,9 +101,13 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_rank_sphere_sharded_step(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["ddp", "overlap"])
+def test_two_rank_sphere_sharded_step(tmp_path, mode):
     world, port = 2, _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), mode), nprocs=world, join=True)
     r0 = torch.load(tmp_path / "rank0.pt")
     r1 = torch.load(tmp_path / "rank1.pt")
     # replicas agree after the all-reduce and after the optimiser step
