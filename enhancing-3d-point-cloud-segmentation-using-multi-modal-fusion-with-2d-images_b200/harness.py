@@ -268,6 +268,11 @@ class OverlappedGradientAverager:
     hides behind the rest of backward; ``finish()`` (call it after ``loss.backward()``) reduces whatever is
     left, waits, and divides by the world size.  No per-parameter hooks, no buckets, no copies.
 
+    STATUS: correct (tests/test_distributed_cpu.py) but NOT the default of bench.py: on 2 B200s the concurrent
+    NCCL kernel slowed the step from 14.0 to 38.8 ms (round 1, one measurement, not yet analysed -- the
+    persistent contraction kernels and the collective compete for the same SMs); the grouped all-reduce
+    after backward stays the default.
+
         avg = OverlappedGradientAverager(net, split_level=3)     # once
         loss.backward(); avg.finish()                            # every step
     """
