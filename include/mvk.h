@@ -228,6 +228,9 @@ int mvk_gemm_f32(const float* A, long long a_rs, long long a_cs, const float* B,
  *                     (momentum, unbiased variance); eval: scale/shift from the running stats.
  * mvk_scale_shift_act out = leaky(y*scale + shift [+ residual]); scale NULL = 1 (bias-only block);
  *                     optional bf16 hi/lo copy (the operand format of mvk_gemm_bf16x3).
+ * Column reductions (mvk_col_stats, mvk_bn_batch_stats, mvk_act_bwd_reduce) run as thread-block clusters:
+ * the CTAs of a cluster fold their partial sums through distributed shared memory and issue one fp64
+ * atomic per column and cluster.
  * mvk_act_bwd_reduce  d = dz * leaky'(pre); sums[c] += d, sums[cols+c] += d * xhat   (fp64)
  * mvk_act_bwd_apply   dy = scale*(d - sum_d/rows - xhat*sum_dxhat/rows)  (batch_stats != 0)
  *                     dy = scale*d                                         (otherwise)
