@@ -102,7 +102,9 @@ def weight_operands(param, rows, cols, src_ld, rows_pad, dst_ld):
     if e.version != param._version or e.epoch != _EPOCH[0]:
         for o in t.entries.values():  # a parameter whose storage moved (.to(), load) must not be read through the old pointer
             p = o.ref()
-            if p is not None and p.data_ptr() != o.src_ptr:
+            if p is None:
+                t.dirty = True  # the parameter is gone: drop its pair at the rebuild below
+            elif p.data_ptr() != o.src_ptr:
                 o.src_ptr = p.data_ptr()
                 t.dirty = True
         if t.dirty:
