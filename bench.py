@@ -255,7 +255,7 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if sample_clocks else None
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None  # one sampler per job, on rank 0
         l0 = L.mvk_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
