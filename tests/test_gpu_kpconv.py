@@ -95,6 +95,134 @@ def test_kpconv_vs_oracle_seeded(mvk, cin, cout, n, strided):
         assert rel_err(conv.weights.grad, wo.grad) < 1e-4, contraction
 
 
+def _oracle_case(mvk, s_pts, lens, q_pts, q_lens, radius, cin, cout, seed, contractions=("fp32", "bf16x3"), crop=None,
+                 oracle_dtype=torch.float64):
+    """One KPConv layer (forward, grad_x, grad_w) on real neighbourhoods against the oracle's restatement of
+    blocks.py:277-374 evaluated in fp64 on the CPU.  Returns {contraction: (H, err_out, err_gx, err_gw)}."""
+    inds = geom.batch_neighbors(q_pts, s_pts, q_lens, lens, radius).astype(np.int64)
+    if crop is not None:
+        inds = np.ascontiguousarray(inds[:, :crop])
+    extent = radius * 1.2 / 2.5
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    conv = mvk.KPConv(15, 3, cin, cout, extent, radius).cuda()
+    n = len(s_pts)
+    x = torch.randn(n, cin)
+    go = torch.randn(len(q_pts), cout)
+    dt = oracle_dtype
+    xo = x.to(dt).requires_grad_(True)
+    wo = conv.weights.detach().cpu().to(dt).requires_grad_(True)
+    oo = modules.kpconv_forward(torch.from_numpy(q_pts).to(dt), torch.from_numpy(s_pts).to(dt), torch.from_numpy(inds), xo,
+                                conv.kernel_points.detach().cpu().to(dt), wo, extent)
+    oo.backward(go.to(dt))
+    res = {}
+    for contraction in contractions:
+        conv.contraction = contraction
+        conv.weights.grad = None
+        xg = x.cuda().requires_grad_(True)
+        out = conv(torch.from_numpy(q_pts).cuda(), torch.from_numpy(s_pts).cuda(), torch.from_numpy(inds).cuda(), xg)
+        out.backward(go.cuda())
+        res[contraction] = (inds.shape[1], rel_err(out, oo), rel_err(xg.grad, xo.grad), rel_err(conv.weights.grad, wo.grad))
+    return res
+
+
+def test_kpconv_driver_smoke_case(mvk):
+    """The exact KPConv cases of __graft_entry__.smoke() (round-1 driver smoke: 64->128 on [4000, 49] neighbour
+    rows = the HCAP=64 stage-A variants + the 3-way auto split-K forward contraction), repeated so that a
+    timing-dependent failure has several chances to show."""
+    rng = np.random.default_rng(0)
+    n = 4000
+    xy = rng.uniform(-1, 1, (n, 2))
+    pts = np.concatenate([xy, (0.1 * np.sin(4 * xy[:, :1]) + rng.normal(0, 0.01, (n, 1)))], 1).astype(np.float32)
+    lens = np.array([1500, 2500], np.int32)
+    radius = 0.12
+    sub, sub_len = geom.grid_subsample_batch(pts, lens, sampleDl=radius / 2.5 * 2)
+    for rep in range(3):
+        r1 = _oracle_case(mvk, pts, lens, pts, lens, radius, 64, 128, seed=0)
+        r2 = _oracle_case(mvk, pts, lens, sub, sub_len, radius, 32, 32, seed=0)
+        for r in (r1, r2):
+            for contraction, (h, e_out, e_gx, e_gw) in r.items():
+                print(f"rep {rep} {contraction} H={h}: {e_out:.2e} {e_gx:.2e} {e_gw:.2e}")
+                assert max(e_out, e_gx, e_gw) < 1e-4, (rep, contraction, h, e_out, e_gx, e_gw)
+    assert r1["bf16x3"][0] == 49
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 64), (64, 128), (128, 128)])  # G = 8, 16, 32 lanes per channel pass
+@pytest.mark.parametrize("width", ["le48", "49to64", "gt64"])             # HCAP=48 / HCAP=64 fast variants / generic kernels
+def test_kpconv_row_width_variants(mvk, cin, cout, width):
+    """Every stage-A kernel variant on cin != cout baseline shapes: neighbour-matrix width H <= 48 (HCAP=48),
+    48 < H <= 64 (HCAP=64) and H > 64 (generic kernels), for each of the three lane groupings."""
+    rng = np.random.default_rng(cin + cout)
+    n = 3000
+    s_pts = bumpy_cloud(rng, n)
+    lens = np.array([n // 3, n - n // 3], np.int32)
+    radius = {"le48": 0.10, "49to64": 0.16, "gt64": 0.20}[width]
+    full = geom.batch_neighbors(s_pts, s_pts, lens, lens, radius).shape[1]
+    crop = {"le48": min(full, 48), "49to64": min(max(full, 49), 64), "gt64": None}[width]
+    if width == "49to64":
+        assert full >= 49, full
+    if width == "gt64":
+        assert full > 64, full
+    res = _oracle_case(mvk, s_pts, lens, s_pts, lens, radius, cin, cout, seed=3, crop=crop)
+    for contraction, (h, e_out, e_gx, e_gw) in res.items():
+        print(f"{cin}->{cout} {width} {contraction} H={h}: {e_out:.2e} {e_gx:.2e} {e_gw:.2e}")
+        if width == "le48":
+            assert h <= 48
+        elif width == "49to64":
+            assert 48 < h <= 64
+        else:
+            assert h > 64
+        assert max(e_out, e_gx, e_gw) < 1e-4, (contraction, h, e_out, e_gx, e_gw)
+
+
+def test_kpconv_config1_layer_vs_oracle(mvk):
+    """BASELINE configs[0]: one rigid 64->128 layer on a ~20k-point cloud, r = 0.10 (KP_extent 0.048), neighbour rows
+    cropped to the p90 width like the reference's neighborhood_limits -- against the fp64 oracle."""
+    rng = np.random.default_rng(11)
+    n = 20000
+    pts = bumpy_cloud(rng, n, extent=2.0)
+    pts[:, :2] *= 0.85  # config-1 density: mean ~31 neighbours within r = 0.10, p90 47 (SURVEY section 8: 30-34 / 39-48)
+    lens = np.array([n], np.int32)
+    full = geom.batch_neighbors(pts, pts, lens, lens, 0.10)
+    counts = (full < n).sum(1)
+    crop = int(np.quantile(counts, 0.9))
+    res = _oracle_case(mvk, pts, lens, pts, lens, 0.10, 64, 128, seed=4, crop=crop)
+    for contraction, (h, e_out, e_gx, e_gw) in res.items():
+        print(f"config1 {contraction} H={h} (uncropped {full.shape[1]}): {e_out:.2e} {e_gx:.2e} {e_gw:.2e}")
+        assert max(e_out, e_gx, e_gw) < 1e-4, (contraction, e_out, e_gx, e_gw)
+
+
+def test_weight_operand_pair(mvk):
+    """The cached bf16 hi/lo pair of a weight matrix: hi + lo reproduces W to 2^-16 relative, before and after an
+    optimiser step (the registry refreshes every registered pair with one launch per step)."""
+    from mvkpconv_b200 import _weights
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(960, 128, device="cuda")), torch.nn.Parameter(torch.randn(480, 32, device="cuda"))]
+    opt = torch.optim.SGD(ps, lr=0.1, fused=True)
+
+    def pair(p):
+        rows, cols = p.shape
+        hi, lo, keep, _ = _weights.weight_operands(p.detach(), rows, cols, cols, rows, cols)
+        torch.cuda.synchronize()
+        raw = keep.cpu()
+        nb = (2 * rows * cols + 255) & ~255
+        off_hi, off_lo = hi - keep.data_ptr(), lo - keep.data_ptr()
+        assert off_lo - off_hi == nb
+        h = raw[off_hi:off_hi + 2 * rows * cols].view(torch.bfloat16).reshape(rows, cols).double()
+        l = raw[off_lo:off_lo + 2 * rows * cols].view(torch.bfloat16).reshape(rows, cols).double()
+        return h, l
+
+    for step in range(3):
+        for p in ps:
+            h, l = pair(p)
+            w = p.detach().cpu().double()
+            assert torch.equal(h.float().bfloat16(), w.float().bfloat16()), "hi must be bf16(W)"
+            assert float((h + l - w).abs().max() / w.abs().max()) < 2 ** -16
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        opt.step()
+
+
 def test_kpconv_linearity_and_shadow_rows(mvk):
     """Size-independent properties at a BASELINE-sized layer (20k points, 64->128): linear in x,
     rows whose neighbours are all shadows are exactly zero."""
