@@ -16,8 +16,15 @@ and the optimiser update.  Metric: stacked input points processed per second (wh
 Weak scaling: every rank gets its own batch of 8 spheres (sharded by sphere); the only collective
 is the DDP gradient all-reduce (NCCL).
 
+The training step is replayed as a CUDA graph (harness.GraphedTrainStep; --no-graphs launches it eagerly).
+Beside the headline the line carries (N = 1): `config0` = BASELINE configs[0] (one rigid 64->128 layer on one
+~20k-point sphere: stage-A HBM fraction, contraction tensor fraction, CPU layer beside it), `neighbors` = the
+radius-neighbour queries/s half of the metric (GPU vs the unmodified reference C++: one thread and P worker
+processes) and `fp32_contraction` = the same step with the strict fp32 contraction.
+
 --impl reference times the reference's CPU path (the unmodified reference C++ in oracle/_ref for
-the pyramid + the torch-CPU restatement of KPConv for the network) on the host cores.
+the pyramid + the torch-CPU restatement of KPConv for the network) on the host cores, on the SAME batch of 8
+spheres.
 """
 import argparse
 import json
@@ -47,6 +54,18 @@ def peaks():
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+WORKLOAD = ("configs[1]: KPConv baseline encoder-decoder (train_ScanNet_baseline shape, 14 KPConv layers, 24.4M params) "
+            "pyramid + fwd + bwd + SGD, one batch of 8 synthetic ScanNet-shaped spheres per GPU")
+
+
+def workload_config(n_pts, limits):
+    """The `config` object of the JSON line -- identical in the B200 arm and the reference arm."""
+    return {"workload": WORKLOAD, "spheres_per_gpu": SPHERES_PER_GPU, "points_per_gpu": int(n_pts), "in_radius": IN_RADIUS,
+            "first_subsampling_dl": FIRST_DL, "K": 15, "neighborhood_limits": [int(v) for v in limits],
+            "parallelism": "one batch of 8 spheres per GPU (N > 1: sphere-sharded, gradient all-reduce)",
+            "l2": "per-step working set (saved [N,15*Cin] operands, >1 GB) far exceeds the 126 MB L2; no flush"}
 
 
 def host_features(pts):
@@ -97,10 +116,29 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def make_batch(rank):
+    """Host side of one rank's batch (untimed): 8 seeded synthetic spheres, stacked; first_subsampling_dl on the GPU."""
+    import mvkpconv_b200 as mvk
+    from mvkpconv_b200 import synthetic
+    sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)
+    spheres = synthetic.make_spheres(SPHERES_PER_GPU, sub, seed=100 * rank, in_radius=IN_RADIUS, first_dl=FIRST_DL)
+    pts_h, lens_h = synthetic.stack(spheres)
+    feats_h = host_features(pts_h)
+    labels_h = np.random.default_rng(rank).integers(0, 20, len(pts_h)).astype(np.int64)
+    return spheres, pts_h, lens_h, feats_h, labels_h
+
+
+def set_contraction(net, contraction):
+    """Every module that contracts on the tensor cores (KPConv incl. nested offset convolutions, UnaryBlock)."""
+    for m in net.modules():
+        if hasattr(m, "contraction"):
+            m.contraction = contraction
+
+
 def run_b200(args):
     import torch.distributed as dist
     import mvkpconv_b200 as mvk
-    from mvkpconv_b200 import _lib, harness, pyramid, synthetic
+    from mvkpconv_b200 import _lib, harness, pyramid
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -125,63 +163,56 @@ def run_b200(args):
     L = _lib.lib()
 
     # ---------------- synthetic batch of this rank (host side, untimed) ----------------
-    sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)  # first_subsampling_dl on the GPU
-    spheres = synthetic.make_spheres(SPHERES_PER_GPU, sub, seed=100 * rank, in_radius=IN_RADIUS, first_dl=FIRST_DL)
-    pts_h, lens_h = synthetic.stack(spheres)
+    spheres, pts_h, lens_h, feats_h, labels_h = make_batch(rank)
     n_pts = len(pts_h)
-    feats_h = host_features(pts_h)
-    labels_h = np.random.default_rng(rank).integers(0, 20, n_pts).astype(np.int64)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     pts_p, feats_p, labels_p, lens_p = pin(pts_h), pin(feats_h), pin(labels_h), pin(lens_h)
 
     cfg = pyramid.baseline_config(in_radius=IN_RADIUS, first_subsampling_dl=FIRST_DL)
     pts_d, lens_d = pts_p.to(dev), lens_p.to(dev)
     cfg.neighborhood_limits = pyramid.calibrate_neighborhood_limits(pts_d, lens_d, cfg)
-    np.random.seed(0)
-    torch.manual_seed(0)
-    net = harness.KPFCNN(cfg).to(dev)
-    for m in net.kpconv_layers():
-        m.contraction = args.contraction
+    feats_d, labels_d = feats_p.to(dev), labels_p.to(dev)
+
+    def build_model(contraction):
+        np.random.seed(0)
+        torch.manual_seed(0)
+        net = harness.KPFCNN(cfg).to(dev)
+        set_contraction(net, contraction)
+        if world > 1 and args.allreduce != "ddp":
+            # identical replicas to start with (DDP would broadcast rank 0's parameters and buffers)
+            with torch.no_grad():  # in-place writes that move the version counters (the bf16 weight pairs key on them)
+                for t in list(net.parameters()) + list(net.buffers()):
+                    dist.broadcast(t, 0)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3, fused=True)
+        return net, opt
+
+    net, opt = build_model(args.contraction)
     model = net
     use_ddp = world > 1 and args.allreduce == "ddp"
     if use_ddp:
         # gradients live inside the all-reduce buckets (no per-step copy); two buckets for ~97 MB of fp32 gradients
         model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
                                                           bucket_cap_mb=64)
-    elif world > 1:
-        # identical replicas to start with (DDP would broadcast rank 0's parameters and buffers)
-        with torch.no_grad():  # in-place writes that move the version counters (the bf16 weight pairs key on them)
-            for t in list(net.parameters()) + list(net.buffers()):
-                dist.broadcast(t, 0)
     grad_params = [p for p in net.parameters() if p.requires_grad]
     averager = harness.OverlappedGradientAverager(net, split_level=3) if (world > 1 and args.allreduce == "overlap") else None
 
-    def allreduce_grads():
-        """Gradient averaging right after backward, without DDP's buckets and per-parameter hooks.
-        'coalesced' (default): ONE grouped NCCL all-reduce over the per-parameter gradient tensors (no flatten /
-        copy-back).  'flat': the tensors are packed into one buffer by a multi-tensor copy, one all-reduce
-        (average) runs on it and the .grad are re-pointed at views of it -- measured no faster at 2 GPUs
-        (13.5 vs 13.3 ms per step), kept for comparison."""
-        if averager is not None:
-            averager.finish()  # the deep levels' gradients have been in flight since the middle of backward
-            return
-        ps = [p for p in grad_params if p.grad is not None]
-        grads = [p.grad for p in ps]
+    def allreduce_grads(grads):
+        """Gradient averaging right after backward, without DDP's buckets and per-parameter hooks: ONE grouped NCCL
+        all-reduce over the per-parameter gradient tensors ('coalesced'), or one all-reduce of a packed copy ('flat')."""
         if args.allreduce == "flat":
             flat = torch.cat([g.reshape(-1) for g in grads])
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            off = 0
-            for p, g in zip(ps, grads):
-                n = g.numel()
-                p.grad = flat[off:off + n].view_as(g)
-                off += n
+            torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
             return
         with dist._coalescing_manager(device=dev, async_ops=False):
             for g in grads:
                 dist.all_reduce(g)
         torch._foreach_div_(grads, float(world))
-    opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.98, weight_decay=1e-3, fused=True)
-    feats_d, labels_d = feats_p.to(dev), labels_p.to(dev)
+
+    graphs_on = (not args.no_graphs) and not use_ddp and averager is None
+    stepper = harness.GraphedTrainStep(net, opt, grad_clip=100.0,
+                                       reduce_grads=allreduce_grads if (world > 1 and not use_ddp and averager is None) else None,
+                                       warm=2 if graphs_on else 10 ** 9)
     queries_per_step = [0]
     host_enqueue_ms = [0.0]
     per_rank = []
@@ -194,42 +225,44 @@ def run_b200(args):
                     (feats_p.to(dev, non_blocking=True), labels_p.to(dev, non_blocking=True)))
         return pts_d, lens_d, (feats_d, labels_d)
 
-    def train(pyr, f, y):
-        batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools,
-                                upsamples=pyr.upsamples, lengths=pyr.lengths, features=f, labels=y)
+    def train(pyr, f, y, st=None):
+        st = st or stepper
         queries_per_step[0] = sum(t.shape[0] for t in pyr.neighbors + pyr.pools + pyr.upsamples)
-        out = model(batch)
-        loss = net.loss(out, y)
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        if world > 1 and not use_ddp:
-            allreduce_grads()
-        torch.nn.utils.clip_grad_value_(grad_params, 100.0)  # utils/trainer.py:191-193
-        opt.step()
-        return loss.detach()
+        if use_ddp or averager is not None:  # comparison modes: eager only
+            batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools,
+                                    upsamples=pyr.upsamples, lengths=pyr.lengths, features=f, labels=y)
+            loss = net.loss(model(batch), y)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if averager is not None:
+                averager.finish()
+            torch.nn.utils.clip_grad_value_(grad_params, 100.0)  # utils/trainer.py:191-193
+            opt.step()
+            return loss.detach()
+        return st(pyr, f, y)
 
-    def step(from_host):
-        """One un-pipelined step (profiling passes and --no-prefetch): pyramid, then training, one stream."""
-        p, ln, (f, y) = load_inputs(from_host)
-        loss = train(pyramid.build_pyramid(p, ln, cfg), f, y)
-        return loss.item() if from_host else loss
+    def step_eager(st=None):
+        """One un-pipelined eager step (per-kernel profiling pass): pyramid, then training, one stream."""
+        p, ln, (f, y) = load_inputs(False)
+        pyr = pyramid.build_pyramid(p, ln, cfg)
+        return (st or stepper).eager(pyr, f, y) if not (use_ddp or averager is not None) else train(pyr, f, y)
 
     prefetch = None if args.no_prefetch else pyramid.PyramidPrefetcher(cfg, dev)
     loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()  # read-back slots of the e2e arm
+    d2h_bytes = loss_pin[0:1].numel() * loss_pin.element_size()
 
-    def run_steps(from_host, steps):
+    def run_steps(from_host, steps, st=None):
         """`steps` steps; with the prefetcher the pyramid of batch i+1 is enqueued on the side stream
         after batch i's training launches, so K steps contain K pyramid builds and K training passes.
         from_host: every step's loss is read back (one step late, so the read never drains the queue)."""
-        if prefetch is None:
-            last = None
-            for _ in range(steps):
-                last = step(from_host)
-            return last
-        last, prev_ev = None, None
+        last, prev_ev, loss = None, None, None
         for i in range(steps):
-            pyr, (f, y) = prefetch.take()
-            loss = train(pyr, f, y)
+            if prefetch is None:
+                p, ln, (f, y) = load_inputs(from_host)
+                pyr = pyramid.build_pyramid(p, ln, cfg)
+            else:
+                pyr, (f, y) = prefetch.take()
+            loss = train(pyr, f, y, st)
             if from_host:
                 slot = loss_pin[i % 2:i % 2 + 1]
                 slot.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -239,28 +272,30 @@ def run_b200(args):
                     prev_ev[0].synchronize()
                     last = float(prev_ev[1])
                 prev_ev = (ev, slot)
-            prefetch.submit(lambda: load_inputs(from_host))
+            if prefetch is not None:
+                prefetch.submit(lambda: load_inputs(from_host))
         if from_host:
             prev_ev[0].synchronize()
             return float(prev_ev[1])
         return loss
 
-    def timed(from_host, steps, warmup, sample_clocks=False):
+    def timed(from_host, steps, warmup, sample_clocks=False, st=None):
+        st = st or stepper
         if prefetch is not None:
             if prefetch._pending is not None:
                 prefetch.take()  # left over from the previous timed region (other input source)
             prefetch.submit(lambda: load_inputs(from_host))
-        run_steps(from_host, warmup)
+        run_steps(from_host, warmup, st)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None  # one sampler per job, on rank 0
-        l0 = L.mvk_launch_count()
+        l0, r0 = L.mvk_launch_count(), st.replays
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         t_host0 = time.perf_counter()
-        last = run_steps(from_host, steps)
+        last = run_steps(from_host, steps, st)
         if prefetch is not None:  # the pyramid enqueued by the last step belongs to the timed region
             torch.cuda.current_stream().wait_stream(prefetch.stream)
         e1.record()
@@ -271,23 +306,38 @@ def run_b200(args):
         torch.cuda.synchronize()
         clocks = sampler.stop() if sampler else None
         ms = e0.elapsed_time(e1)
+        # kernels launched in the region: eager launches pass through the C ABI (counted there); a graph replay
+        # launches the kernels that were counted once when the graph was captured
+        launches = (L.mvk_launch_count() - l0) + (st.replays - r0) * (st.launches_per_step or 0)
         if world > 1:
             mine = torch.tensor([ms, float(n_pts)], device=dev)
             allr = [torch.zeros_like(mine) for _ in range(world)]
             dist.all_gather(allr, mine)
             per_rank[:] = [(round(float(a[0]) / steps, 3), int(a[1])) for a in allr]
             ms = max(float(a[0]) for a in allr)  # the job is as slow as its slowest rank
-        return ms, L.mvk_launch_count() - l0, clocks, float(last)
+        return ms, launches, clocks, float(last)
 
+    if graphs_on:
+        # set-up, not warm-up: two eager steps (optimiser state, weight-operand registry, kernel attributes) and the
+        # capture of the step's graph; the W warm-up steps below are replays like the timed ones
+        if prefetch is not None:
+            prefetch.submit(lambda: load_inputs(False))
+        run_steps(False, 3)
+        torch.cuda.synchronize()
     ms, launches, clocks, loss_v = timed(False, args.steps, args.warmup, sample_clocks=True)
     enqueue_ms = host_enqueue_ms[0]
     ranks_info = list(per_rank)
     if args.quick:  # profiling runs (ncu): only the device-resident timed region
         if rank == 0:
             print(json.dumps({"quick": True, "ms_per_step": round(ms / args.steps, 3), "points": n_pts,
-                              "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(enqueue_ms, 3)}), flush=True)
+                              "gpu_launches": int(launches), "host_enqueue_ms_per_step": round(enqueue_ms, 3),
+                              "graphs": bool(graphs_on)}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     ms_e2e, _, _, _ = timed(True, args.steps, max(1, args.warmup // 2))
+    enqueue_e2e_ms = host_enqueue_ms[0]
 
     # ---------------- per-kernel timing inside a timed region (roofline) ----------------
     torch.cuda.synchronize()
@@ -295,7 +345,7 @@ def run_b200(args):
         pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         pe0.record()
         for _ in range(args.steps):
-            step(False)
+            step_eager()
         pe1.record()
         torch.cuda.synchronize()
     prof_ms = pe0.elapsed_time(pe1)
@@ -313,6 +363,12 @@ def run_b200(args):
         if name == "mvk_kpconv_weighted_bwd":
             nq, is64, h, cin, ld = a[1], a[5], a[6], a[7], a[14]
             return "stage_a_bwd", f"[cin={cin}]", nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * ld), 0.0
+        if name == "mvk_kpconv_fused":
+            nq, is64, h, cin, cout, save = a[1], a[5], a[6], a[8], a[12], nz(a[17])
+            kd = 15 * cin
+            return ("kpconv_fused_fwd", f"[cin={cin},cout={cout}]",
+                    nq * (h * ((8 if is64 else 4) + 12 + 4 * cin) + 12 + 4 * cout + (4 * kd if save else 0)) + 4.0 * kd * cout,
+                    2.0 * nq * kd * cout * 3)
         if name == "mvk_gemm_bf16x3":
             M, N, K, nv, terms = a[8], a[9], a[10], a[13], a[14]
             ob = 4 if terms == 3 else 2  # bytes per operand element (hi + lo, or hi only)
@@ -370,63 +426,99 @@ def run_b200(args):
                 "frac_of_mixed_roofline": round(f["ideal_ms"] / f["ms"], 4)}
 
     KERNEL_OF = {"stage_a_fwd": "kp_fwd_fast / kp_fwd_tiny (mvk_kpconv_weighted)", "stage_a_bwd": "kp_bwd_fast (mvk_kpconv_weighted_bwd)",
+                 "kpconv_fused_fwd": "kp_fused_fwd (mvk_kpconv_fused: gather + influence + tcgen05 contraction)",
                  "contraction": "gemm_tc_kernel (mvk_gemm_bf16x3)", "bn_stats": "col_stats_kernel (mvk_bn_batch_stats)",
                  "bn_act_fwd": "scale_shift_act_kernel (mvk_scale_shift_act)", "bn_act_bwd_reduce": "act_bwd_reduce_kernel",
                  "bn_act_bwd_apply": "act_bwd_apply_kernel", "operand_split": "split_bf16_vec4 (mvk_split_bf16)",
                  "neighbors": "k_query (mvk_neighbors_query_capped)"}
     rooflines = {k: roof(KERNEL_OF.get(k, k), f) for k, f in fam.items() if f["bytes"] > 0 or f["flops"] > 0}
-    top = max(rooflines.items(), key=lambda kv: fam[kv[0]]["ms"], default=(None, None))
-    roofline = top[1]
-    # DRAM traffic per launch of the dominant kernel from the committed ncu capture (profiles/), if any
+    # measured DRAM / L2 traffic per launch of each family from the committed ncu captures (profiles/traffic.json)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if roofline is not None and top[0] in tr:
-            roofline["traffic"] = tr[top[0]]["dram_bytes_per_launch"]
-            roofline["traffic_source"] = tr[top[0]]["source"]
-            roofline["algorithmic_bytes_per_launch"] = round(fam[top[0]]["bytes"] / fam[top[0]]["calls"], 1)
     except Exception:
-        pass
+        tr = {}
+    for k, r in rooflines.items():
+        r["algorithmic_bytes_per_launch"] = round(fam[k]["bytes"] / fam[k]["calls"], 1)
+        if k in tr:
+            r["traffic"] = tr[k].get("dram_bytes_per_launch")
+            r["l2_bytes_per_launch"] = tr[k].get("l2_bytes_per_launch")
+            r["traffic_source"] = tr[k].get("source")
+            if tr[k].get("dram_gbs") is not None:  # ncu-measured DRAM bandwidth of the largest launches of the family
+                r["ncu_dram_frac"] = round(tr[k]["dram_gbs"] / pk["hbm_gbs"], 4)
+    top = max(rooflines.items(), key=lambda kv: fam[kv[0]]["ms"], default=(None, None))
+    roofline = top[1]
     breakdown = {n: {"ms_per_step": round(v[0] / args.steps, 3), "calls_per_step": v[1] // args.steps}
                  for n, v in sorted(by_entry.items(), key=lambda kv: -kv[1][0])}
     nb_ms = sum(v[0] for n, v in by_entry.items() if n.startswith("mvk_neighbors"))
     nb_qps = queries_per_step[0] * args.steps / (nb_ms * 1e-3) if nb_ms > 0 else None
+
+    # ---------------- the same step with the strict fp32 contraction (N = 1) ----------------
+    fp32_line = None
+    if world == 1 and args.contraction != "fp32" and not args.no_extras:
+        del stepper.graphs
+        stepper.graphs = {}
+        net32, opt32 = build_model("fp32")
+        st32 = harness.GraphedTrainStep(net32, opt32, grad_clip=100.0, warm=2 if graphs_on else 10 ** 9)
+        k32 = max(3, args.steps // 2)
+        if prefetch is not None and prefetch._pending is None:
+            prefetch.submit(lambda: load_inputs(False))
+        run_steps(False, 3, st32)  # set-up: eager warm steps + capture
+        ms32, launches32, _, loss32 = timed(False, k32, 3, st=st32)
+        fp32_line = {"contraction": "fp32", "dtype": "f32", "value": round(n_pts * k32 / (ms32 * 1e-3), 1), "unit": UNIT,
+                     "ms_per_step": round(ms32 / k32, 3), "steps": k32, "gpu_launches": int(launches32), "loss": loss32,
+                     "what": "same workload, strict fp32 FFMA contraction (csrc/gemm_simt.cu): the path with network-level "
+                             "1e-4 parity (tests/test_gpu_network.py)"}
+        del st32, net32, opt32
+        torch.cuda.empty_cache()
 
     total_pts = n_pts  # weak scaling: every rank holds its own 8 spheres (sizes differ slightly by seed)
     if world > 1:
         t = torch.tensor([float(n_pts)], device=dev)
         dist.all_reduce(t)
         total_pts = int(t.item())
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras["config0"] = bench_config0(dev, pk, pk_kind, cpu=not args.no_cpu_baseline)
+        extras["neighbors"] = bench_neighbors(dev, pts_h, lens_h, pk, cpu=not args.no_cpu_baseline)
     if rank == 0:
         h2d = pts_p.numel() * 4 + feats_p.numel() * 4 + labels_p.numel() * 8 + lens_p.numel() * 4
+        dtype = {"bf16x3": "bf16x3", "bf16": "bf16", "fp32": "f32"}[args.contraction]
         line = {
             "metric": METRIC, "value": round(total_pts * args.steps / (ms * 1e-3), 1), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype,
+            "dtype_note": {"bf16x3": "contractions on tcgen05 with bf16 hi/lo split operands (3 MMA terms, fp32 accumulate): "
+                                     "per-operator error ~5e-6 of max|ref| (bar 1e-4); everything else fp32",
+                           "bf16": "plain bf16 tensor-core contractions (stated separately: 2e-2)",
+                           "fp32": "strict fp32 FFMA contractions"}[args.contraction],
             "contraction": args.contraction, "data": "synthetic",
-            "config": {"workload": "configs[1]: KPConv baseline encoder-decoder (train_ScanNet_baseline shape, 14 KPConv "
-                                   "layers, 24.4M params) pyramid + fwd + bwd + SGD, 8 synthetic spheres/GPU",
-                       "spheres_per_gpu": SPHERES_PER_GPU, "points_per_gpu": n_pts, "in_radius": IN_RADIUS,
-                       "first_subsampling_dl": FIRST_DL, "K": 15, "neighborhood_limits": cfg.neighborhood_limits,
-                       "parallelism": (f"sphere-sharded x{world}, gradient all-reduce (NCCL, {args.allreduce})" if world > 1 else "single GPU"),
-                       "pipeline": ("one stream: pyramid, forward, backward, SGD in sequence" if args.no_prefetch else
-                                    "pyramid of batch i+1 built on a side stream while batch i trains "
-                                    "(K timed steps = K pyramids + K training passes)"),
-                       "l2": "per-step working set (saved [N,15*Cin] operands, >1 GB) far exceeds the 126 MB L2; no flush"},
+            "config": workload_config(n_pts, cfg.neighborhood_limits),
+            "impl_notes": {
+                "parallelism": (f"sphere-sharded x{world}, gradient all-reduce (NCCL, {args.allreduce})" if world > 1 else "single GPU"),
+                "pipeline": ("one stream: pyramid, forward, backward, SGD in sequence" if args.no_prefetch else
+                             "pyramid of batch i+1 built on a side stream while batch i trains "
+                             "(K timed steps = K pyramids + K training passes)"),
+                "launch": ("training step replayed as a CUDA graph (captured once per pyramid shape signature); pyramid eager"
+                           if graphs_on else "eager launches")},
             "e2e": {"value": round(total_pts * args.steps / (ms_e2e * 1e-3), 1), "unit": UNIT,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": 4 + 4 * 15},
+                    "d2h_bytes_per_step": int(d2h_bytes), "host_enqueue_ms_per_step": round(enqueue_e2e_ms, 3)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
+            "rooflines_note": "per C-ABI call, CUDA events on the launching stream, in an eager un-pipelined pass of the same step",
             "neighbor_queries_per_s": round(nb_qps, 1) if nb_qps else None,
             "neighbor_queries_per_step": int(queries_per_step[0]),
             "breakdown_ms": breakdown, "loss": loss_v, "host_enqueue_ms_per_step": round(enqueue_ms, 3),
         }
+        if fp32_line:
+            line["fp32_contraction"] = fp32_line
+        line.update(extras)
         if ranks_info:
             line["per_rank_ms_and_points"] = ranks_info
         if args.detail:
             det = sorted(agg.items(), key=lambda kv: -kv[1][0])[:args.detail]
             line["detail_us_per_call"] = {k: [round(1e3 * v[0] / v[1], 1), v[1] // args.steps] for k, v in det}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference(steps=2, warmup=1, seed=0)
+            line["cpu_baseline"] = cpu_reference(steps=1, warmup=1, seed=0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -434,18 +526,178 @@ def run_b200(args):
 
 
 # =================================================================================================
+# BASELINE configs[0] and the queries/s half of the metric (N = 1 extras of the same JSON line)
+# =================================================================================================
+def _time_rotating(fn, sets, iters):
+    """Average ms of fn(set) over `iters` calls cycling through `sets` (distinct input/output buffers whose combined
+    footprint exceeds the 126 MB L2: every call starts with cold caches without a flush kernel in the timing)."""
+    for s in sets:
+        fn(s)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(sets[i % len(sets)])
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def bench_config0(dev, pk, pk_kind, cpu=True):
+    """BASELINE configs[0]: ONE rigid KPConv layer 64 -> 128 on ONE synthetic sphere (r = 2 m, dl = 0.04, ~20-40k points,
+    K = 15, conv radius 0.10, rows cropped to the p90 width like neighborhood_limits), forward and forward+backward.
+    Roofline fractions per SURVEY section 8(d): stage A against HBM with B_gi = H (idx + 12 + 4 Cin) + 12 bytes per point
+    (+ 4*15*Cin written when the weighted operand is staged), contraction against the tensor pipe with
+    F_c = 2*15*Cin*Cout flop per point (x3 MMA terms executed for bf16x3)."""
+    import mvkpconv_b200 as mvk
+    from mvkpconv_b200 import _lib, synthetic
+    from mvkpconv_b200._lib import check, ptr, stream_ptr
+    L = _lib.lib()
+    sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)
+    pts = synthetic.make_spheres(1, sub, seed=0, in_radius=IN_RADIUS, first_dl=FIRST_DL)[0]
+    n = len(pts)
+    lens = np.array([n], np.int32)
+    r, cin, cout, K = 2.5 * FIRST_DL, 64, 128, 15
+    extent = r * 1.2 / 2.5
+    p_d, l_d = torch.from_numpy(pts).to(dev), torch.from_numpy(lens).to(dev)
+    full, counts = mvk.batch_neighbors(p_d, p_d, l_d, l_d, r, return_counts=True)
+    H = max(1, int(torch.quantile(counts.float().cpu(), 0.9).item()))
+    inds = full[:, :H].contiguous().long()
+    np.random.seed(0)
+    torch.manual_seed(0)
+    conv = mvk.KPConv(K, 3, cin, cout, extent, r).to(dev)
+    nsets = 6  # 6 x (x 5-10 MB + saved operand ~75-150 MB) >> L2
+    sets = [SimpleNamespace(x=torch.randn(n, cin, device=dev), go=torch.randn(n, cout, device=dev)) for _ in range(nsets)]
+
+    def fwd(s):
+        with torch.no_grad():
+            return conv(p_d, p_d, inds, s.x)
+
+    def fwd_bwd(s):
+        x = s.x.requires_grad_(True)
+        conv.weights.grad = None
+        x.grad = None
+        conv(p_d, p_d, inds, x).backward(s.go)
+
+    ms_f = _time_rotating(fwd, sets, 30)
+    ms_fb = _time_rotating(fwd_bwd, sets, 30)
+    # per-kernel durations (CUDA events around each C-ABI call, eager)
+    with _lib.profile() as rec:
+        for i in range(12):
+            fwd_bwd(sets[i % nsets])
+        torch.cuda.synchronize()
+    per = {}
+    for name, a, s, e in rec:
+        per.setdefault(name, []).append(s.elapsed_time(e))
+    med = {k: float(np.median(v)) for k, v in per.items()}
+    kd = K * cin
+    b_gi = H * (8 + 12 + 4 * cin) + 12
+    hbm, tc = pk["hbm_gbs"] * 1e9, pk["bf16_tflops_sustained"] * 1e12
+    out = {"workload": "configs[0]: single rigid KPConv layer 64->128 on one synthetic ScanNet sphere (r=2 m, dl=0.04, K=15)",
+           "points": n, "H": H, "H_uncropped": int(full.shape[1]), "contraction": conv.contraction,
+           "fwd": {"points_per_s": round(n / (ms_f * 1e-3), 1), "ms": round(ms_f, 4)},
+           "fwd_bwd": {"points_per_s": round(n / (ms_fb * 1e-3), 1), "ms": round(ms_fb, 4)},
+           "l2": f"{nsets} rotating input/output sets (footprint > 126 MB L2)",
+           "kernel_us": {k: round(1e3 * v, 2) for k, v in med.items()}, "peak_kind": pk_kind}
+    if "mvk_kpconv_fused" in med:
+        t = med["mvk_kpconv_fused"] * 1e-3
+        out["fused_fwd"] = {"B_gi_bytes_per_point": b_gi + 4 * cout, "hbm_frac": round(n * (b_gi + 4 * cout) / t / hbm, 4),
+                            "F_c_flop_per_point": 2 * kd * cout, "tensor_frac_useful": round(n * 2.0 * kd * cout / t / tc, 4),
+                            "tensor_frac_executed": round(n * 6.0 * kd * cout / t / tc, 4)}
+    if "mvk_kpconv_weighted" in med:
+        t = med["mvk_kpconv_weighted"] * 1e-3
+        out["stage_a_fwd"] = {"B_gi_bytes_per_point": b_gi, "staged_bytes_per_point": 4 * kd,
+                              "hbm_frac_B_gi": round(n * b_gi / t / hbm, 4),
+                              "hbm_frac_with_staged_write": round(n * (b_gi + 4 * kd) / t / hbm, 4)}
+    if "mvk_kpconv_weighted_bwd" in med:
+        t = med["mvk_kpconv_weighted_bwd"] * 1e-3
+        out["stage_a_bwd"] = {"hbm_frac_B_gi": round(n * b_gi / t / hbm, 4),
+                              "hbm_frac_with_staged_read": round(n * (b_gi + 4 * kd) / t / hbm, 4)}
+    if "mvk_gemm_bf16x3" in per:
+        # forward A.W, dW = A^T dOut, dA = dOut W^T: three launches per fwd+bwd, in call order
+        calls = [(a, s.elapsed_time(e)) for name, a, s, e in rec if name == "mvk_gemm_bf16x3"]
+        per_step = len(calls) // 12
+        names = ["fwd A.W", "dW = A^T.dOut", "dA = dOut.W^T"] if per_step == 3 else ["dW = A^T.dOut", "dA = dOut.W^T"]
+        gem = {}
+        for j, nm in enumerate(names):
+            ts = [calls[i * per_step + j][1] for i in range(12)]
+            t = float(np.median(ts)) * 1e-3
+            gem[nm] = {"us": round(t * 1e6, 2), "tensor_frac_useful": round(n * 2.0 * kd * cout / t / tc, 4),
+                       "tensor_frac_executed_3_terms": round(n * 6.0 * kd * cout / t / tc, 4),
+                       "hbm_frac_operands": round((4.0 * n * kd + 4.0 * kd * cout + 4.0 * n * cout) / t / hbm, 4)}
+        out["contraction"] = gem
+    if cpu:
+        from oracle import cpu_bench
+        out["cpu"] = cpu_bench.kpconv_layer_cpu(pts, inds.cpu().numpy(), sets[0].x.detach().cpu().numpy(),
+                                                conv.kernel_points.detach().cpu().numpy(),
+                                                conv.weights.detach().cpu().numpy(), extent)
+    return out
+
+
+def bench_neighbors(dev, pts_h, lens_h, pk, cpu=True):
+    """Radius-neighbour queries/s on the stacked batch (8 spheres, ~267k queries = supports, r = 0.10: the level-0
+    conv-neighbour call of the pyramid) through the reference-facing `batch_neighbors` (count + fill, uncapped rows:
+    the reference's semantics), with inputs resident in HBM and end to end from host numpy arrays; the unmodified
+    reference C++ (nanoflann) is timed beside it, one thread per call and P worker processes."""
+    import mvkpconv_b200 as mvk
+    r = 2.5 * FIRST_DL
+    p_d, l_d = torch.from_numpy(pts_h).to(dev), torch.from_numpy(lens_h).to(dev)
+    n = len(pts_h)
+    w = [0]
+
+    def resident():
+        w[0] = mvk.batch_neighbors(p_d, p_d, l_d, l_d, r).shape[1]
+
+    def host():
+        mvk.batch_neighbors(pts_h, pts_h, lens_h, lens_h, r)
+
+    def wall(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters
+
+    t_res, t_host = wall(resident, 10), wall(host, 5)
+    alg = 12.0 * n + 12.0 * n + 4.0 * n * w[0]
+    out = {"queries": n, "radius": r, "row_width": int(w[0]),
+           "resident": {"queries_per_s": round(n / t_res, 1), "ms": round(1e3 * t_res, 3),
+                        "hbm_frac_algorithmic": round(alg / t_res / (pk["hbm_gbs"] * 1e9), 4)},
+           "e2e_host_arrays": {"queries_per_s": round(n / t_host, 1), "ms": round(1e3 * t_host, 3),
+                               "what": "numpy in -> H2D -> count + fill -> D2H numpy out (the reference's calling convention)"}}
+    if cpu:
+        import tempfile
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "nbr.npz")
+            np.savez(path, points=pts_h, lengths=lens_h, radius=np.float32(r))
+            res = subprocess.run([sys.executable, "-m", "oracle.cpu_bench", "neighbors", path], cwd=ROOT,
+                                 capture_output=True, text=True, timeout=600)
+        try:
+            out["cpu"] = json.loads(res.stdout.strip().splitlines()[-1])
+            out["speedup_vs_cpu_single_thread"] = round(out["e2e_host_arrays"]["queries_per_s"] /
+                                                        out["cpu"]["single_thread"]["queries_per_s"], 1)
+            out["speedup_vs_cpu_worker_processes"] = round(out["e2e_host_arrays"]["queries_per_s"] /
+                                                           out["cpu"]["worker_processes"]["queries_per_s"], 1)
+        except Exception as e:  # noqa: BLE001
+            out["cpu"] = {"error": repr(e), "stderr": res.stderr[-300:]}
+    return out
+
+
+# =================================================================================================
 # CPU reference arm / cpu_baseline leg.  The ONLY code in this file that touches oracle/.
 # =================================================================================================
-def cpu_reference(steps, warmup, seed=0, n_spheres=1):
-    """The reference's CPU path on a bounded sample of the workload: `n_spheres` of the batch's
-    spheres; pyramid by the unmodified reference C++ (oracle/_ref, one thread like the reference's
-    workers), network forward+backward+SGD on torch CPU with all host threads."""
+def cpu_reference(steps, warmup, seed=0, n_spheres=SPHERES_PER_GPU):
+    """The reference's CPU path on the SAME workload as the B200 arm (the batch of 8 seeded spheres of rank 0):
+    pyramid by the unmodified reference C++ (oracle/_ref, one thread like the reference's workers), network
+    forward + backward + SGD on torch CPU with all host threads through the oracle's restatement of KPConv."""
     from mvkpconv_b200 import harness, pyramid, synthetic
     from oracle import geom, modules
 
-    kind = "reference" if geom.have_ref() else "port"
-    nbr = geom.ref_batch_neighbors if geom.have_ref() else geom.batch_neighbors
-    gsub = geom.ref_grid_subsample_batch if geom.have_ref() else geom.grid_subsample_batch
+    have_ref = geom.have_ref()
+    nbr = geom.ref_batch_neighbors if have_ref else geom.batch_neighbors
+    gsub = geom.ref_grid_subsample_batch if have_ref else geom.grid_subsample_batch
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     sub = lambda p, dl: gsub(p, np.array([len(p)], np.int32), sampleDl=dl)[0]
@@ -494,11 +746,16 @@ def cpu_reference(steps, warmup, seed=0, n_spheres=1):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {"value": round(len(pts) * steps / dt, 1), "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{n_spheres} of the {SPHERES_PER_GPU} spheres of one batch ({len(pts)} points), {steps} steps after "
-                      f"{warmup} warm-up; pyramid: unmodified reference C++ (1 thread), network: torch CPU ({cores} threads)",
+    return {"value": round(len(pts) * steps / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "kind_detail": ("pyramid (radius neighbours, grid subsampling) = the UNMODIFIED reference C++ compiled from "
+                            "/root/reference (oracle/_ref/libref.so); " if have_ref else "pyramid = the plain-C restatement; ")
+                           + "network = torch-CPU restatement of the reference graph (oracle.modules.KPConvOracle + torch "
+                             "Linear / BatchNorm1d / LeakyReLU), not the reference's own Python files (absent on the GPU box)",
+            "sample": f"the whole batch: {n_spheres} of {SPHERES_PER_GPU} spheres ({len(pts)} points), {steps} step(s) after "
+                      f"{warmup} warm-up; pyramid 1 thread (like a reference DataLoader worker), network {cores} threads",
             "ms_per_step": round(1e3 * dt / steps, 1), "ms_pyramid": round(1e3 * t_pyr / steps, 1),
-            "ms_network": round(1e3 * t_net / steps, 1), "points": int(len(pts))}
+            "ms_network": round(1e3 * t_net / steps, 1), "points": int(len(pts)),
+            "neighborhood_limits": [int(v) for v in cfg.neighborhood_limits]}
 
 
 def run_reference(args):
@@ -506,14 +763,14 @@ def run_reference(args):
     if rank != 0:
         return  # rank 0 alone runs the CPU reference; the other ranks exit 0 without work
     world = int(os.environ.get("WORLD_SIZE", args.gpus))
-    base = cpu_reference(steps=args.steps, warmup=args.warmup, seed=0)
+    steps, warmup = args.steps, args.warmup  # one CPU step of the full batch takes ~10 s on 16 cores
+    base = cpu_reference(steps=steps, warmup=warmup, seed=0)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+        "steps": steps, "warmup": warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: KPConv baseline encoder-decoder (train_ScanNet_baseline shape, 14 KPConv "
-                               "layers, 24.4M params) pyramid + fwd + bwd + SGD; CPU arm on a bounded sample",
-                   "in_radius": IN_RADIUS, "first_subsampling_dl": FIRST_DL, "K": 15},
+        "config": workload_config(base["points"], base["neighborhood_limits"]),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -530,6 +787,9 @@ def main():
     ap.add_argument("--contraction", default=os.environ.get("MVK_CONTRACTION", "bf16x3"),
                     choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch the training step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the config0 / neighbours / fp32-contraction legs of the N = 1 line")
     ap.add_argument("--allreduce", default="coalesced", choices=["coalesced", "overlap", "flat", "ddp"],
                     help="N > 1: gradients packed into one buffer + ONE NCCL all-reduce (flat), a grouped all-reduce of the "
                          "per-parameter tensors (coalesced), or torch DDP buckets (ddp)")

@@ -329,3 +329,121 @@ class OverlappedGradientAverager:
         grads = [p.grad for p in self.params if p.grad is not None]
         if grads:
             torch._foreach_div_(grads, float(self.world))
+
+
+class GraphedTrainStep:
+    """One training step (forward, loss, backward, gradient clipping, optimiser update) replayed as a CUDA graph.
+
+    The eager step is ~590 short launches issued from Python (autograd Functions, scratch allocations, tensor-map
+    encodes): the host needs as long to enqueue it as the B200 needs to run it.  Once the shapes of a batch are
+    known -- the pyramid's level sizes and row widths -- nothing in the step depends on the host any more, so the
+    whole launch sequence is captured once per shape signature and replayed with one ``cudaGraphLaunch``.  The
+    pyramid itself (data-dependent sizes, a few read-backs) stays eager on its side stream; its tensors are copied
+    into the graph's static input buffers (a few hundred MB of device-to-device traffic, < 0.1 ms).
+
+    * ``signature`` = shapes / dtypes of every pyramid tensor + features + labels.  A batch with a new signature
+      runs eagerly the first ``warm`` times it is seen (optimiser state, weight-operand registry and kernel
+      attributes must exist before a capture) and is captured afterwards; ``max_graphs`` signatures are kept
+      (least recently used first out), each with its own memory pool.  A loader that pads its level sizes to
+      buckets keeps the number of signatures small.
+    * single rank: ONE graph holds forward + backward + clip + optimiser step.  ``reduce_grads`` given (sharded
+      job): graph A = forward + backward, then ``reduce_grads(list of gradient tensors)`` runs eagerly (NCCL), then
+      graph B = clip + optimiser step.
+    * the optimiser must be capture-safe with its state already initialised (``torch.optim.SGD(fused=True)`` with
+      a float learning rate bakes the rate into the graph; use a tensor ``lr`` to schedule it).
+    """
+
+    def __init__(self, net, optimizer, grad_clip=100.0, reduce_grads=None, max_graphs=4, warm=2):
+        from collections import OrderedDict
+        self.net, self.opt, self.grad_clip, self.reduce_grads = net, optimizer, grad_clip, reduce_grads
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        self.graphs = OrderedDict()
+        self.seen = {}
+        self.max_graphs, self.warm = max_graphs, warm
+        self.launches_per_step = None  # libmvk launches captured per step (replays do not pass through the C ABI)
+        self.replays = 0
+
+    @staticmethod
+    def signature(pyr, features, labels):
+        sig = []
+        for lst in (pyr.points, pyr.neighbors, pyr.pools, pyr.upsamples, pyr.lengths):
+            sig.append(tuple((tuple(t.shape), str(t.dtype)) for t in lst))
+        sig.append((tuple(features.shape), str(features.dtype), tuple(labels.shape), str(labels.dtype)))
+        return tuple(sig)
+
+    def _finish(self, grads=None):
+        if self.reduce_grads is not None:
+            self.reduce_grads(grads if grads is not None else [p.grad for p in self.params if p.grad is not None])
+        if self.grad_clip:
+            torch.nn.utils.clip_grad_value_(self.params, self.grad_clip)  # utils/trainer.py:191-193
+        self.opt.step()
+
+    def eager(self, pyr, features, labels):
+        batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools, upsamples=pyr.upsamples,
+                                lengths=pyr.lengths, features=features, labels=labels)
+        loss = self.net.loss(self.net(batch), labels)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        self._finish()
+        return loss.detach()
+
+    def _capture(self, pyr, features, labels):
+        from . import _lib
+        clone = lambda lst: [t.clone() for t in lst]
+        static = SimpleNamespace(points=clone(pyr.points), neighbors=clone(pyr.neighbors), pools=clone(pyr.pools),
+                                 upsamples=clone(pyr.upsamples), lengths=clone(pyr.lengths), features=features.clone(),
+                                 labels=labels.clone())
+        L = _lib.lib()
+        entry = SimpleNamespace(static=static, graph_a=torch.cuda.CUDAGraph(), graph_b=None, loss=None, grads=None)
+        self.opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        _lib._ZEROS.buf = None  # zero-initialised scratch must be allocated (and re-zeroed on replay) inside the graph
+        l0 = L.mvk_launch_count()
+        with torch.cuda.graph(entry.graph_a):
+            loss = self.net.loss(self.net(static), static.labels)
+            loss.backward()
+            if self.reduce_grads is None:
+                self._finish()
+            entry.loss = loss.detach()
+        _lib._ZEROS.buf = None
+        entry.grads = [p.grad for p in self.params if p.grad is not None]
+        if self.reduce_grads is not None:
+            entry.graph_b = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(entry.graph_b):
+                if self.grad_clip:
+                    torch.nn.utils.clip_grad_value_(self.params, self.grad_clip)
+                self.opt.step()
+            _lib._ZEROS.buf = None
+        self.launches_per_step = int(L.mvk_launch_count() - l0)
+        return entry
+
+    def __call__(self, pyr, features, labels):
+        """Runs one step on (pyramid, features, labels); returns the loss (a device scalar that the next call
+        overwrites -- read or copy it before)."""
+        from . import _weights
+        sig = self.signature(pyr, features, labels)
+        entry = self.graphs.get(sig)
+        if entry is None:
+            n = self.seen.get(sig, 0)
+            self.seen[sig] = n + 1
+            if n < self.warm:
+                return self.eager(pyr, features, labels)
+            entry = self._capture(pyr, features, labels)  # records only; the static buffers hold this batch already
+            self.graphs[sig] = entry
+            while len(self.graphs) > self.max_graphs:
+                self.graphs.popitem(last=False)
+        else:
+            self.graphs.move_to_end(sig)
+            st = entry.static
+            for dst, src in ((st.points, pyr.points), (st.neighbors, pyr.neighbors), (st.pools, pyr.pools),
+                             (st.upsamples, pyr.upsamples), (st.lengths, pyr.lengths)):
+                torch._foreach_copy_(dst, src)
+            st.features.copy_(features)
+            st.labels.copy_(labels)
+        entry.graph_a.replay()
+        if entry.graph_b is not None:
+            self.reduce_grads(entry.grads)
+            entry.graph_b.replay()
+        self.replays += 1
+        _weights.invalidate()  # the parameters moved without passing through torch.optim's step hook
+        return entry.loss

@@ -113,3 +113,70 @@ def test_kpfcnn_step_vs_cpu_oracle(mvk, modulated, contraction):
     for k, b in bc.items():
         if k.endswith("running_var"):
             assert rel_err(bg[k], b) < tol, k
+
+
+def test_graphed_train_step_matches_eager(mvk):
+    """harness.GraphedTrainStep (CUDA-graph replay of forward + loss + backward + clip + SGD) against the same
+    steps launched eagerly: identical batches, identical initial parameters, 10 steps over two shape signatures.
+    The losses of every step agree to 1e-4; the final parameters agree as closely as two EAGER runs agree with each
+    other (fp32 atomics in the scatter kernels reorder sums from run to run, which shows in near-cancelling
+    parameters such as batch-norm biases): bar = max(1e-4, 4 x the eager-vs-eager difference) per tensor."""
+    from mvkpconv_b200 import harness, pyramid
+    rng = np.random.default_rng(7)
+    dev = torch.device("cuda")
+    arch = ['simple', 'resnetb', 'resnetb_strided', 'resnetb', 'resnetb_strided', 'resnetb',
+            'nearest_upsample', 'unary', 'nearest_upsample', 'unary']
+    cfg = pyramid.baseline_config(architecture=arch, first_subsampling_dl=0.03, first_features_dim=32, num_classes=6,
+                                  in_features_dim=2)
+    batches = []
+    for b in range(2):  # two batches with DIFFERENT shapes: two signatures, two graphs
+        n1, n2 = 1500 + 200 * b, 1200
+        pts = np.concatenate([cloud(rng, n1), cloud(rng, n2)], 0)
+        lens = np.array([n1, n2], np.int32)
+        feats = np.concatenate([np.ones((len(pts), 1), np.float32), pts[:, 2:3]], 1)
+        labels = rng.integers(0, 6, len(pts)).astype(np.int64)
+        pyr = pyramid.build_pyramid(torch.from_numpy(pts).to(dev), torch.from_numpy(lens).to(dev), cfg,
+                                    random_grid_orient=False)
+        batches.append((pyr, torch.from_numpy(feats).to(dev), torch.from_numpy(labels).to(dev)))
+
+    def make():
+        np.random.seed(0)
+        torch.manual_seed(0)
+        net = harness.KPFCNN(cfg).cuda()
+        opt = torch.optim.SGD(net.parameters(), lr=1e-2, momentum=0.9, weight_decay=1e-3, fused=True)
+        return net, opt
+
+    order = [0, 1, 0, 1, 0, 1, 0, 0, 1, 1]
+    net_e, opt_e = make()
+    eager = harness.GraphedTrainStep(net_e, opt_e, warm=10 ** 9)  # never captures
+    losses_e = [float(eager(*batches[i])) for i in order]
+    net_e2, opt_e2 = make()
+    eager2 = harness.GraphedTrainStep(net_e2, opt_e2, warm=10 ** 9)
+    for i in order:
+        eager2(*batches[i])
+    net_g, opt_g = make()
+    graphed = harness.GraphedTrainStep(net_g, opt_g, warm=2)
+    losses_g = [float(graphed(*batches[i])) for i in order]
+    assert len(graphed.graphs) == 2 and graphed.replays == len(order) - 4
+    assert graphed.launches_per_step and graphed.launches_per_step > 50
+    for a, b in zip(losses_e, losses_g):
+        assert abs(a - b) < 1e-4 * abs(a), (losses_e, losses_g)
+    worst = 0.0
+    for (k, pe), (_, pg), (_, pe2) in zip(net_e.named_parameters(), net_g.named_parameters(), net_e2.named_parameters()):
+        floor = rel_err(pe2, pe)
+        worst = max(worst, rel_err(pg, pe))
+        assert rel_err(pg, pe) < max(1e-4, 4 * floor), (k, rel_err(pg, pe), floor)
+    print("graph vs eager, worst parameter tensor:", worst)
+    for (k, be), (_, bg), (_, be2) in zip(net_e.named_buffers(), net_g.named_buffers(), net_e2.named_buffers()):
+        if be.dtype.is_floating_point:
+            assert rel_err(bg, be) < max(1e-4, 4 * rel_err(be2, be)), k
+        else:
+            assert torch.equal(be, bg), k  # num_batches_tracked advances inside the replayed kernels too
+    # an eager consumer after the replays sees the CURRENT weights (the bf16 operand pairs are invalidated)
+    net_g.eval(); net_e.eval()
+    pyr, f, y = batches[0]
+    from types import SimpleNamespace as NS
+    mk = lambda: NS(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools, upsamples=pyr.upsamples,
+                    lengths=pyr.lengths, features=f)
+    with torch.no_grad():
+        assert rel_err(net_g(mk()), net_e(mk())) < 1e-3
