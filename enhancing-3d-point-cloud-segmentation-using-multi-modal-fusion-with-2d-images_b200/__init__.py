@@ -25,10 +25,11 @@ from .geometry import batch_grid_subsampling, batch_neighbors, create_3D_rotatio
 from .kernel_points import load_kernels  # noqa: F401
 from .blocks import BatchNormBlock, UnaryBlock, bn_act, softmax_cross_entropy  # noqa: F401
 from .kpconv import KPConv, closest_pool, gather, max_pool  # noqa: F401
-from .lifting import FeatureAggregation, depth2xyz, group_points, knn_pixels, unproject_views  # noqa: F401
+from .lifting import (FeatureAggregation, depth2xyz, group_points, knn_pixels, knn_pixels_batched,  # noqa: F401
+                      unproject_views, unproject_views_batched)
 
 __all__ = [
     "KPConv", "UnaryBlock", "BatchNormBlock", "bn_act", "softmax_cross_entropy", "max_pool", "closest_pool", "gather", "batch_neighbors", "grid_subsampling",
     "batch_grid_subsampling", "group_points", "FeatureAggregation", "depth2xyz", "unproject_views",
-    "knn_pixels", "load_kernels", "create_3D_rotations",
+    "knn_pixels", "knn_pixels_batched", "unproject_views_batched", "load_kernels", "create_3D_rotations",
 ]

@@ -301,8 +301,10 @@ int mvk_kpconv_deform_weighted(const float* q_pts, int nq, const float* s_pts, i
             influence, aggregation};
     const int hcap = (h + 3) & ~3;
     const size_t per_warp = (size_t)KD * 16 + (size_t)KD * hcap * 8 + KD * 4;
-    if (per_warp * 4 > 200 * 1024) return MVK_ERR_RANGE;
-    const int wpb = 4;
+    // wide neighbourhoods (deform_radius = 6 makes rows 5-6x wider than the rigid ones): fewer warps per CTA
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;
+    if (per_warp * wpb > 200 * 1024) return MVK_ERR_RANGE;
     const size_t smem = per_warp * wpb;
     int blocks = (nq + wpb - 1) / wpb;
     const int maxb = num_sms() * 16;
@@ -336,8 +338,9 @@ int mvk_kpconv_deform_weighted_bwd(const float* q_pts, int nq, const float* s_pt
             influence, aggregation};
     const int hcap = (h + 3) & ~3;
     const size_t per_warp = (size_t)KD * 16 + (size_t)KD * hcap * 24 + KD * 4;
-    if (per_warp * 4 > 200 * 1024) return MVK_ERR_RANGE;
-    const int wpb = 4;
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > 200 * 1024) wpb >>= 1;  // rows up to ~530 wide with one warp per CTA
+    if (per_warp * wpb > 200 * 1024) return MVK_ERR_RANGE;
     const size_t smem = per_warp * wpb;
     int blocks = (nq + wpb - 1) / wpb;
     const int maxb = num_sms() * 16;

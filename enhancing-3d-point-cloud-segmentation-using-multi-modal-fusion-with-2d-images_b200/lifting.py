@@ -306,3 +306,106 @@ def knn_pixels(xyz64, mask, queries, k=3):
         ws = _workspace(wsb, dev)
         check(L.mvk_knn_pixels(ptr(keys), ptr(m), npix, ptr(q), nq, k, ptr(ws), ws.numel(), ptr(out), stream_ptr()))
     return out.cpu().numpy() if as_np else out
+
+
+# -------------------------------------------------------------------------------------------------
+# Batched lifting: all spheres of a stacked batch at once (replaces the per-sphere loops of
+# ScanNet_sphere_color.py:409-452 and architectures_sphere.py:246-279)
+# -------------------------------------------------------------------------------------------------
+def unproject_views_batched(cam_matrices, depths, poses):
+    """Every view of every sphere of a batch in one launch.
+
+    cam_matrices (B, 4, 4) or (4, 4) float32 (already rescaled to the depth resolution, :370-372),
+    depths (B, nv, h, w) float32 metres, poses (B, nv, 4, 4) camera -> world.
+    Returns (image_xyz [B, nv, h, w, 3] f32 -- the reference's batch.image_xyz --, mask [B, nv, h, w] bool,
+    xyz64 [B*nv*h*w, 3] f64 -- what the reference feeds to the kNN)."""
+    _lib.require_cuda()
+    L = _lib.lib()
+    d = depths if isinstance(depths, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(depths, dtype=np.float32))
+    d = d.cuda().contiguous().float()
+    B, nv, h, w = d.shape
+    dev = d.device
+    P = poses if isinstance(poses, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(poses, dtype=np.float32))
+    P = P.to(dev).contiguous().float().reshape(B * nv, 16)
+    cam = cam_matrices.detach().cpu().numpy() if isinstance(cam_matrices, torch.Tensor) else np.asarray(cam_matrices)
+    cam = np.broadcast_to(cam.reshape(-1, 4, 4) if cam.ndim == 3 else cam[None], (B, 4, 4))
+    # inv() on the host in fp32 like the reference (one 3x3 per sphere), widened to fp64, one copy per view
+    kinv = np.stack([_kinv64(c) for c in cam], 0)
+    kinv = torch.from_numpy(np.ascontiguousarray(np.repeat(kinv, nv, axis=0).reshape(B * nv, 9))).to(dev)
+    xyz64 = torch.empty((B * nv * h * w, 3), dtype=torch.float64, device=dev)
+    xyz32 = torch.empty((B, nv, h, w, 3), dtype=torch.float32, device=dev)
+    mask = torch.empty((B, nv, h, w), dtype=torch.uint8, device=dev)
+    with _lib.on_device(dev):
+        check(L.mvk_unproject_views_batched(ptr(kinv), ptr(d), ptr(P), B * nv, h, w, ptr(xyz64), ptr(xyz32), ptr(mask),
+                                            stream_ptr()))
+    return xyz32, mask.bool(), xyz64
+
+
+def knn_pixels_batched(xyz64, image_xyz, mask, queries, q_lengths, k=3, grid_dim=64, cell_min=0.02, global_ids=False,
+                       return_far=False):
+    """k nearest valid pixels of every stacked sphere point among the pixels of its own sphere's views.
+
+    xyz64 [B*npix, 3] f64, image_xyz [B, nv, h, w, 3] f32, mask [B, nv, h, w] (all three from
+    unproject_views_batched), queries [N, 3] f32 world-frame sphere points (the reference's feat_aggre_points),
+    q_lengths [B] i32.  Returns int64 [N, k]: pixel ids local to the sphere (the reference's knn_list entries,
+    ScanNet_sphere_color.py:452) or global (b * nv*h*w + id) with global_ids=True; identical to knn_pixels run
+    sphere by sphere."""
+    _lib.require_cuda()
+    L = _lib.lib()
+    dev = xyz64.device
+    B = image_xyz.shape[0]
+    npix = image_xyz.shape[1] * image_xyz.shape[2] * image_xyz.shape[3]
+    x32 = image_xyz.reshape(-1, 3).contiguous().float()
+    m = mask.reshape(-1).to(torch.uint8).contiguous()
+    q = queries.to(dev).reshape(-1, 3).contiguous().float()
+    ql = (q_lengths if isinstance(q_lengths, torch.Tensor) else torch.as_tensor(np.asarray(q_lengths, np.int32)))
+    ql = ql.to(dev).to(torch.int32).contiguous()
+    nq = q.shape[0]
+    out = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    far = torch.zeros(B, dtype=torch.int32, device=dev) if return_far else None
+    with _lib.on_device(dev):
+        wsb = L.mvk_knn_batched_workspace_bytes(B, npix, nq, grid_dim)
+        ws = _workspace(wsb, dev, "knn")
+        check(L.mvk_knn_pixels_batched(ptr(xyz64), ptr(x32), ptr(m), B, npix, ptr(q), ptr(ql), nq, k, grid_dim,
+                                       float(cell_min), 1 if global_ids else 0, ptr(ws), ws.numel(), ptr(out), ptr(far),
+                                       stream_ptr()))
+    return (out, far) if return_far else out
+
+
+def _fa_forward_from_views(self, feature_2d, image_xyz, knn_global, tgt_points, differentiable=None):
+    """FeatureAggregation over a whole stacked batch without materialising the grouped tensors.
+
+    feature_2d  (V, C, h, w)   the 2D network's output for all V = B*nv views (any memory format; constant)
+    image_xyz   (V*h*w, 3) or (B, nv, h, w, 3) float32 world coordinates of the pixels
+    knn_global  (np, k)        int64 global pixel ids (view * h*w + pix)
+    tgt_points  (np, 3)        float32 world-frame sphere points
+    returns     (C_out, np)
+    differentiable: None = gradients to the module's parameters when autograd would need them (late fusion);
+    False = constant path (early / middle fusion detach the lifted features, architectures_sphere.py:288)."""
+    _lib.require_cuda()
+    L = _lib.lib()
+    V, c, h, w = feature_2d.shape
+    np_, k = knn_global.shape
+    dev = feature_2d.device
+    if feature_2d.requires_grad and torch.is_grad_enabled():
+        raise RuntimeError("forward_from_views treats the 2D feature map as a constant (the 2D network is frozen in "
+                           "MV-KPConv, architectures_sphere.py:233-237)")
+    grad_path = self._needs_grad() if differentiable is None else bool(differentiable)
+    with torch.no_grad(), torch.cuda.device(dev):
+        f = feature_2d.detach()
+        if f.dtype is not torch.float32:
+            f = f.float()
+        X = torch.empty((np_ * k, c + 4), dtype=torch.float32, device=dev)
+        xyz_c = image_xyz.reshape(-1, 3).contiguous().float()
+        knn_c, tgt_c = knn_global.contiguous().long(), tgt_points.reshape(-1, 3).contiguous().float()
+        # pixel stride: the (h, w) plane must be addressable by one flat index
+        if f.stride(2) != w * f.stride(3):
+            f = f.contiguous()
+        check(L.mvk_fa_gather_views(f.data_ptr(), f.stride(0), f.stride(1), f.stride(3), c, h * w, ptr(xyz_c), ptr(knn_c),
+                                    np_, k, ptr(tgt_c), ptr(X), c + 4, stream_ptr()))
+        if not grad_path:
+            return self._run(X, np_, k)
+    return self._run_autograd(X, np_, k)
+
+
+FeatureAggregation.forward_from_views = _fa_forward_from_views

@@ -333,6 +333,35 @@ int mvk_fa_gather(const float* feat2d, long long chan_stride, long long pix_stri
 int mvk_fa_reduce(const float* Y, int np, int k, int cout, const float* scale, const float* shift,
                   int reduction, float* out, mvk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched lifting: all spheres of a stacked batch in one launch set.  Replaces the per-sphere Python loop of
+ * the fusion nets (KPConv-PyTorch/models/architectures_sphere.py:246-279, same loop in
+ * architectures_sphere_middle_fusion.py and architectures_sphere_late_fusion.py) and the per-sphere numpy /
+ * sklearn work of get_rgbd_data (datasets/ScanNet_sphere_color.py:409-452).
+ * ---------------------------------------------------------------------------------------------- */
+/* Like mvk_unproject_views with ONE inverse intrinsics matrix PER VIEW: kinv [nviews, 9] f64. */
+int mvk_unproject_views_batched(const double* kinv, const float* depth, const float* pose, int nviews, int h, int w,
+                                double* xyz64, float* xyz32, unsigned char* mask, mvk_stream_t stream);
+size_t mvk_knn_batched_workspace_bytes(int nb, int npix_per_element, int nq, int grid_dim);
+/* k nearest valid pixels of every query among the pixels of ITS batch element: xyz64 / xyz32 / mask are
+ * [nb * npix_per_element, ...] (element b owns pixels [b*npix, (b+1)*npix)), queries [nq,3] f32 stacked with
+ * q_lengths [nb] i32 (device).  Per-element uniform grid of grid_dim^3 cells (cell edge >= cell_min) + exact
+ * ring search + exhaustive pass for unresolved queries; fp64 distances, ties by lower pixel id: the same result
+ * as mvk_knn_pixels run per element.  out [nq,k] i64: pixel ids local to the element (view*h*w + pix, the
+ * reference's knn_list[i]) or, with global_ids != 0, offset by b*npix (what mvk_fa_gather_views consumes);
+ * -1 where the element has fewer than k valid pixels.  far_counts [nb] i32 (device, may be NULL): queries per
+ * element that needed the exhaustive pass. */
+int mvk_knn_pixels_batched(const double* xyz64, const float* xyz32, const unsigned char* mask, int nb,
+                           int npix_per_element, const float* queries, const int* q_lengths, int nq, int k,
+                           int grid_dim, float cell_min, int global_ids, void* ws, size_t ws_bytes, long long* out,
+                           int* far_counts, mvk_stream_t stream);
+/* mvk_fa_gather for a whole batch: feat = the 2D network's output [views, c, h*w] addressed through
+ * (view_stride, chan_stride, pix_stride) in elements (NCHW or channels-last), knn_global [np,k] global pixel
+ * ids (view * hw + pix), xyz32 [views*hw, 3], tgt_xyz [np,3] the stacked sphere points. */
+int mvk_fa_gather_views(const float* feat, long long view_stride, long long chan_stride, long long pix_stride, int c,
+                        int hw, const float* xyz32, const long long* knn_global, int np, int k, const float* tgt_xyz,
+                        float* X, int ldx, mvk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

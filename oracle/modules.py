@@ -219,3 +219,38 @@ class KPConvOracle(torch.nn.Module):
             return out
         return kpconv_forward(q_pts, s_pts, neighb_inds, x, self.kernel_points, self.weights, self.KP_extent,
                               self.KP_influence, self.aggregation_mode)
+
+
+class FeatureAggregationOracle(torch.nn.Module):
+    """mvpnet/models/mvpnet_3d.py:12-70 with the reference's module structure and parameter names
+    (mlp.{i}.conv.weight, mlp.{i}.bn.*): SharedMLP(ndim=2) = [Conv2d 1x1 no bias, BatchNorm2d, ReLU] x 3
+    (common/nn/modules/mlp.py:38-75, conv.py:29-51), xavier-uniform conv weights (mvpnet_3d.py:66-70)."""
+
+    class _Layer(torch.nn.Module):
+        def __init__(self, cin, cout):
+            super().__init__()
+            self.conv = torch.nn.Conv2d(cin, cout, 1, bias=False)
+            self.bn = torch.nn.BatchNorm2d(cout)
+
+        def forward(self, x):
+            return torch.relu(self.bn(self.conv(x)))
+
+    def __init__(self, in_channels, mlp_channels=(64, 64, 64), reduction="sum", use_relation=True):
+        super().__init__()
+        assert use_relation
+        self.reduction = reduction
+        self.mlp = torch.nn.ModuleList()
+        c = in_channels + 4
+        for co in mlp_channels:
+            self.mlp.append(self._Layer(c, co))
+            c = co
+        for m in self.modules():
+            if isinstance(m, torch.nn.Conv2d):
+                torch.nn.init.xavier_uniform_(m.weight)
+
+    def forward(self, src_xyz, tgt_xyz, feature):
+        diff = src_xyz - tgt_xyz.unsqueeze(-1)
+        x = torch.cat([feature, diff, torch.sum(diff ** 2, dim=1, keepdim=True)], dim=1)
+        for layer in self.mlp:
+            x = layer(x)
+        return torch.sum(x, 3) if self.reduction == "sum" else torch.max(x, 3)[0]
