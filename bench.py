@@ -480,6 +480,16 @@ def run_b200(args):
     if world == 1 and not args.no_extras:
         extras["config0"] = bench_config0(dev, pk, pk_kind, cpu=not args.no_cpu_baseline)
         extras["neighbors"] = bench_neighbors(dev, pts_h, lens_h, pk, cpu=not args.no_cpu_baseline)
+        stepper.graphs = {}
+        torch.cuda.empty_cache()
+        try:
+            r2 = run_fusion(args, "early", steps=max(3, args.steps // 2), warmup=3, emit=False)
+            extras["config2"] = {k: r2[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "lifting_ms", "gpu_launches", "config")}
+            r4 = run_scene(args, emit=False)
+            extras["config4"] = {k: r4[k] for k in ("metric", "value", "unit", "ms_per_step", "scene_points_per_s",
+                                                    "neighbor_queries_per_s", "config")}
+        except Exception as e:  # noqa: BLE001  (the headline must not die with an extra)
+            extras["config2_4_error"] = repr(e)[:300]
     if rank == 0:
         h2d = pts_p.numel() * 4 + feats_p.numel() * 4 + labels_p.numel() * 8 + lens_p.numel() * 4
         dtype = {"bf16x3": "bf16x3", "bf16": "bf16", "fp32": "f32"}[args.contraction]
@@ -523,6 +533,266 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# =================================================================================================
+# Fusion workloads (BASELINE configs[2], configs[3]) and the whole-scene sweep (configs[4])
+# =================================================================================================
+FUSION_VIEWS = {"early": 3, "middle": 5, "late": 5}
+
+
+def run_fusion(args, fusion, steps=None, warmup=None, emit=True):
+    """MV-KPConv fusion step on one batch of 8 synthetic spheres with nv synthetic 160x120 views each (early: 3 views,
+    configs[2]; middle / late: 5 views, configs[3]): frozen UNet-ResNet34 on the B*nv images, batched lifting
+    (unprojection + per-sphere grid 3-NN + FeatureAggregation over the whole stacked batch), fusion KPFCNN forward +
+    loss + backward + SGD.  N > 1: sphere-sharded like the baseline, gradient all-reduce after backward."""
+    import torch.distributed as dist
+    import mvkpconv_b200 as mvk
+    from mvkpconv_b200 import _lib, fusion as fu, harness, pyramid, synthetic
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    steps, warmup = steps or args.steps, warmup or args.warmup
+    nv, h, w = FUSION_VIEWS[fusion], 120, 160
+    L = _lib.lib()
+    sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)
+    sph = synthetic.make_fusion_spheres(SPHERES_PER_GPU, sub, seed=100 * rank, in_radius=IN_RADIUS, first_dl=FIRST_DL,
+                                        n_views=nv, h=h, w=w)
+    pts_h = np.concatenate([s.points for s in sph], 0)
+    world_h = np.concatenate([s.world for s in sph], 0)
+    lens_h = np.array([len(s.points) for s in sph], np.int32)
+    n_pts = len(pts_h)
+    rng = np.random.default_rng(rank)
+    labels_h = rng.integers(0, 20, n_pts).astype(np.int64)
+    images_h = rng.normal(0, 1, (SPHERES_PER_GPU, nv, 3, h, w)).astype(np.float32)
+    depths_h = np.stack([s.depths for s in sph], 0)
+    poses_h = np.stack([s.poses for s in sph], 0)
+    cams_h = np.stack([s.cam for s in sph], 0)
+    f3d_h = (np.concatenate([np.ones((n_pts, 1), np.float32), world_h[:, 2:3]], 1) if fusion == "early" else
+             np.concatenate([np.ones((n_pts, 1), np.float32), world_h], 1)).astype(np.float32)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    host = {k: pin(v) for k, v in dict(pts=pts_h, world=world_h, lens=lens_h, labels=labels_h, images=images_h,
+                                       depths=depths_h, poses=poses_h, f3d=f3d_h).items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    cfg = fu.fusion_config(fusion, in_radius=IN_RADIUS, first_subsampling_dl=FIRST_DL)
+    cfg.neighborhood_limits = pyramid.calibrate_neighborhood_limits(resident["pts"], resident["lens"], cfg)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = fu.FusionKPFCNN(cfg, fusion=fusion, precision_2d=args.precision_2d).to(dev)
+    set_contraction(net, args.contraction)
+    if world > 1:
+        with torch.no_grad():
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t, 0)
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=1e-2, momentum=0.98, weight_decay=1e-3, fused=True)
+
+    def allreduce_grads(grads):
+        with dist._coalescing_manager(device=dev, async_ops=False):
+            for g in grads:
+                dist.all_reduce(g)
+        torch._foreach_div_(grads, float(world))
+
+    graphs_on = not args.no_graphs
+    stepper = harness.GraphedTrainStep(net, opt, grad_clip=100.0, reduce_grads=allreduce_grads if world > 1 else None,
+                                       warm=2 if graphs_on else 10 ** 9)
+    from mvkpconv_b200 import lifting
+    kinv = lifting.intrinsics_inverse(cams_h, SPHERES_PER_GPU, nv, dev)  # fixed intrinsics: inverted once
+
+    def one_step(from_host):
+        np.random.seed(1)
+        src = {k: v.to(dev, non_blocking=True) for k, v in host.items()} if from_host else resident
+        pyr = pyramid.build_pyramid(src["pts"], src["lens"], cfg)
+        # the numeric half of get_rgbd_data for the whole batch: unprojection + 3-NN on the GPU
+        xyz32, _, knn = fu.prepare_lifting(cams_h, src["depths"], src["poses"], src["world"], src["lens"], kinv=kinv)
+        extras = dict(images=src["images"], image_xyz=xyz32, knn_global=knn, feat_aggre_points=src["world"],
+                      feature_3d=src["f3d"])
+        return stepper(pyr, src["f3d"], src["labels"], extras)
+
+    def timed(from_host, k, wu):
+        for _ in range(wu):
+            one_step(from_host)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0, r0 = L.mvk_launch_count(), stepper.replays
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(k):
+            loss = one_step(from_host)
+            if from_host:
+                last = loss.item()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = (L.mvk_launch_count() - l0) + (stepper.replays - r0) * (stepper.launches_per_step or 0)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, float(loss if last is None else last)
+
+    for _ in range(3):  # set-up: eager warm steps + capture
+        one_step(False)
+    sampler = ClockSampler(local) if (emit and rank == 0) else None
+    ms, launches, loss_v = timed(False, steps, warmup)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, _, _ = timed(True, steps, max(1, warmup // 2))
+    # lifting alone (unprojection + kNN + 2D net + FeatureAggregation), resident
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    net.eval()
+    e0.record()
+    for _ in range(5):
+        xyz32, _, knn = fu.prepare_lifting(cams_h, resident["depths"], resident["poses"], resident["world"], resident["lens"],
+                                           kinv=kinv)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_prep = e0.elapsed_time(e1) / 5
+    b = SimpleNamespace(images=resident["images"], image_xyz=xyz32, knn_global=knn, feat_aggre_points=resident["world"])
+    with torch.no_grad():
+        net.lift(b)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            net.lift(b)
+        e1.record()
+        torch.cuda.synchronize()
+    ms_lift = e0.elapsed_time(e1) / 5
+    net.train()
+    total_pts = n_pts
+    if world > 1:
+        t = torch.tensor([float(n_pts)], device=dev)
+        dist.all_reduce(t)
+        total_pts = int(t.item())
+    res = {
+        "metric": "MV-KPConv %s-fusion fwd+bwd points/s" % fusion, "value": round(total_pts * steps / (ms * 1e-3), 1),
+        "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16x3": "bf16x3", "bf16": "bf16", "fp32": "f32"}[args.contraction], "data": "synthetic",
+        "config": {"workload": "configs[%d]: MV-KPConv %s fusion, %d synthetic 160x120 views per sphere + UNet-ResNet34 64-d "
+                               "features lifted to the sphere points, fwd+bwd+SGD, 8 spheres/GPU" % (2 if fusion == "early" else 3, fusion, nv),
+                   "spheres_per_gpu": SPHERES_PER_GPU, "points_per_gpu": n_pts, "views": nv, "image_hw": [h, w],
+                   "neighborhood_limits": [int(v) for v in cfg.neighborhood_limits], "precision_2d": args.precision_2d,
+                   "l2": "per-step working set > 1 GB; no flush"},
+        "e2e": {"value": round(total_pts * steps / (ms_e2e * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms_e2e / steps, 3),
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches), "clocks": clocks, "loss": loss_v,
+        "lifting_ms": {"unproject_plus_knn": round(ms_prep, 3), "unet_plus_feature_aggregation": round(ms_lift, 3),
+                       "pixels": int(SPHERES_PER_GPU * nv * h * w), "points": n_pts},
+    }
+    if emit and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_bench
+        s0 = sph[0]
+        feat2d = np.random.default_rng(0).normal(0, 1, (nv, 64, h, w)).astype(np.float32)
+        wts = [np.random.default_rng(i).normal(0, 0.1, sh).astype(np.float32) for i, sh in enumerate([(64, 68), (64, 64), (64, 64)])]
+        res["cpu_lifting"] = cpu_bench.lifting_cpu(s0.cam, s0.depths, s0.poses, feat2d, s0.world, wts, iters=1)
+    if emit and rank == 0:
+        print(json.dumps(res), flush=True)
+    if emit and world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
+
+
+def run_scene(args, emit=True):
+    """BASELINE configs[4]: inference sweep over a synthetic ~200k-point scene (dl = 0.04): a fixed lattice of
+    overlapping r = 2 m spheres, per batch of spheres the 5-level pyramid (grid subsampling + radius search) and the
+    KPConv stack (eval mode), votes accumulated per point; spheres sharded round-robin over the ranks, ONE all-reduce
+    of the vote table at the end.  Strong scaling: the scene is fixed."""
+    import torch.distributed as dist
+    import mvkpconv_b200 as mvk
+    from mvkpconv_b200 import harness, pyramid, scene, synthetic
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    room = synthetic.make_room(seed=7, density=9000.0, size=(12.0, 8.0, 2.6), n_boxes=16)
+    pts = mvk.grid_subsampling(room, sampleDl=FIRST_DL)
+    cfg = pyramid.baseline_config(in_radius=IN_RADIUS, first_subsampling_dl=FIRST_DL)
+    centers = scene.sphere_centers(pts, IN_RADIUS, spacing=IN_RADIUS, z=1.0)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = harness.KPFCNN(cfg).to(dev)
+    set_contraction(net, args.contraction)
+    # neighbourhood limits from the first batch of spheres (the reference calibrates them on its sampler)
+    sw0 = scene.SceneSweep(net, cfg, spheres_per_batch=SPHERES_PER_GPU)
+    scene_t = torch.from_numpy(pts).to(dev)
+    _, centred, lengths = sw0.crop(scene_t, torch.from_numpy(centers[:SPHERES_PER_GPU]).to(dev))
+    lengths = lengths[lengths > 0]
+    cfg.neighborhood_limits = pyramid.calibrate_neighborhood_limits(centred, lengths, cfg)
+    sweep = scene.SceneSweep(net, cfg, spheres_per_batch=SPHERES_PER_GPU)
+    steps, warmup = max(1, args.steps // 2), 2
+    for _ in range(warmup):
+        sweep.run(scene_t, centers, rank, world)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sweep.stats = SimpleNamespace(batches=0, spheres=0, points=0, queries=0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        probs, counts = sweep.run(scene_t, centers, rank, world)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    st = torch.tensor([ms, float(sweep.stats.points), float(sweep.stats.queries), float(sweep.stats.spheres)], device=dev)
+    if world > 1:
+        mx = st.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(st)
+        ms = float(mx[0])
+    sphere_pts, queries, spheres = float(st[1]) / steps, float(st[2]) / steps, float(st[3]) / steps
+    res = {"metric": "whole-scene sweep sphere-points/s", "value": round(sphere_pts * steps / (ms * 1e-3), 1), "unit": UNIT,
+           "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": round(ms / steps, 3), "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": {"bf16x3": "bf16x3", "bf16": "bf16", "fp32": "f32"}[args.contraction],
+           "data": "synthetic",
+           "config": {"workload": "configs[4]: whole-scene inference sweep, synthetic 12x8 m scene at dl=0.04, lattice of r=2 m "
+                                  "spheres, multi-level grid subsampling + radius search + KPConv stack (eval), sphere-sharded",
+                      "scene_points": int(len(pts)), "spheres": int(len(centers)), "sphere_points_per_sweep": int(sphere_pts),
+                      "neighbor_queries_per_sweep": int(queries), "covered": float((counts > 0).float().mean()),
+                      "l2": "every batch of spheres streams > 1 GB of operands; no flush"},
+           "scene_points_per_s": round(len(pts) * steps / (ms * 1e-3), 1),
+           "neighbor_queries_per_s": round(queries * steps / (ms * 1e-3), 1), "gpu_launches": None}
+    if emit and rank == 0:
+        print(json.dumps(res), flush=True)
+    if emit and world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return res
 
 
 # =================================================================================================
@@ -788,6 +1058,10 @@ def main():
                     choices=["bf16x3", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch the training step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--workload", default="baseline", choices=["baseline", "early", "middle", "late", "scene"],
+                    help="baseline = BASELINE configs[1] (the headline); early = configs[2]; middle / late = configs[3]; "
+                         "scene = configs[4] (whole-scene sweep)")
+    ap.add_argument("--precision-2d", default="fp32", choices=["fp32", "bf16"], help="autocast of the frozen 2D network")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the config0 / neighbours / fp32-contraction legs of the N = 1 line")
     ap.add_argument("--allreduce", default="coalesced", choices=["coalesced", "overlap", "flat", "ddp"],
@@ -803,6 +1077,10 @@ def main():
         args.warmup = 3  # timing rule: W >= 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload in ("early", "middle", "late"):
+        run_fusion(args, args.workload)
+    elif args.workload == "scene":
+        run_scene(args)
     else:
         run_b200(args)
 

@@ -40,12 +40,12 @@ except ImportError:  # pragma: no cover  (older torch: version counters / explic
 
 
 class _Entry:
-    __slots__ = ("ref", "key", "buf", "hi", "lo", "version", "src_ptr", "epoch")
+    __slots__ = ("ref", "key", "buf", "hi", "lo", "version", "src_ptr", "epoch", "offset")
 
 
 class _DeviceTable:
     def __init__(self):
-        self.entries = {}     # id(param) -> _Entry
+        self.entries = {}     # (id(owner), byte offset of the view, key) -> _Entry
         self.table = None     # device copy of the descriptor array
         self.order = []
         self.chunks = 0
@@ -78,35 +78,62 @@ def _rebuild(t, device):
     t.dirty = False
 
 
+def _capturing():
+    try:
+        return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+    except Exception:  # pragma: no cover
+        return False
+
+
+def _owner(param):
+    """The long-lived tensor a weight operand belongs to: the parameter itself, or the base of a view of it
+    (``conv.weight.reshape(cout, -1)`` is a new tensor object on every call; its base is the parameter)."""
+    base = getattr(param, "_base", None)
+    return base if base is not None else param
+
+
 def weight_operands(param, rows, cols, src_ld, rows_pad, dst_ld):
     """(hi pointer, lo pointer, keep-alive tensor, version) of the bf16 pair of ``param`` viewed as
-    [rows, cols] with row pitch src_ld, zero-padded to [rows_pad, dst_ld].  ``param`` must be fp32 contiguous."""
+    [rows, cols] with row pitch src_ld, zero-padded to [rows_pad, dst_ld].  ``param`` must be fp32 contiguous
+    (a parameter or a view of one)."""
     L = _lib.lib()
     dev = param.device
     t = _table(dev)
     key = (int(rows), int(cols), int(src_ld), int(rows_pad), int(dst_ld))
-    e = t.entries.get(id(param))
+    owner = _owner(param)
     src_ptr = param.data_ptr()
-    if e is None or e.ref() is not param or e.key != key or e.src_ptr != src_ptr:
+    offset = src_ptr - owner.data_ptr()
+    ekey = (id(owner), offset, key)
+    e = t.entries.get(ekey)
+    if e is None or e.ref() is not owner:
         e = _Entry()
-        e.ref, e.key, e.src_ptr = weakref.ref(param), key, src_ptr
+        e.ref, e.key, e.src_ptr, e.offset = weakref.ref(owner), key, src_ptr, offset
         n = 2 * rows_pad * dst_ld
         nb = (n + 255) & ~255
         e.buf = torch.empty(2 * nb, dtype=torch.uint8, device=dev)
         e.hi, e.lo = e.buf.data_ptr(), e.buf.data_ptr() + nb
         check(L.mvk_split_bf16(src_ptr, rows, cols, src_ld, e.hi, e.lo, rows_pad, dst_ld, stream_ptr()))
         e.version, e.epoch = param._version, _EPOCH[0]
-        t.entries[id(param)] = e
+        t.entries[ekey] = e
         t.dirty = True
         return e.hi, e.lo, e.buf, e.version
-    if e.version != param._version or e.epoch != _EPOCH[0]:
+    if e.version != param._version or e.epoch != _EPOCH[0] or e.src_ptr != src_ptr:
         for o in t.entries.values():  # a parameter whose storage moved (.to(), load) must not be read through the old pointer
             p = o.ref()
             if p is None:
                 t.dirty = True  # the parameter is gone: drop its pair at the rebuild below
-            elif p.data_ptr() != o.src_ptr:
-                o.src_ptr = p.data_ptr()
+            elif p.data_ptr() + o.offset != o.src_ptr:
+                o.src_ptr = p.data_ptr() + o.offset
                 t.dirty = True
+        if t.dirty and _capturing():
+            # the descriptor table cannot be uploaded inside a stream capture: refresh pair by pair (captured launches)
+            for o in t.entries.values():
+                p = o.ref()
+                if p is not None:
+                    r, c, sld, rp, dld = o.key
+                    check(L.mvk_split_bf16(o.src_ptr, r, c, sld, o.hi, o.lo, rp, dld, stream_ptr()))
+                    o.version, o.epoch = p._version, _EPOCH[0]
+            return e.hi, e.lo, e.buf, e.version
         if t.dirty:
             _rebuild(t, dev)
         check(L.mvk_split_bf16_multi(t.table.data_ptr(), len(t.order), t.chunks, stream_ptr()))

@@ -98,10 +98,11 @@ class UNetResNet34(nn.Module):
 
 
 # -------------------------------------------------------------------------------------------------
-def prepare_lifting(cam_matrices, depths, poses, feat_aggre_points, lengths, k=3):
+def prepare_lifting(cam_matrices, depths, poses, feat_aggre_points, lengths, k=3, kinv=None):
     """The numeric half of ``get_rgbd_data`` (ScanNet_sphere_color.py:409-452) for a whole batch on the GPU:
-    returns (image_xyz [B, nv, h, w, 3] f32, image_mask [B, nv, h, w] bool, knn_global [N, k] int64)."""
-    xyz32, mask, xyz64 = _lift.unproject_views_batched(cam_matrices, depths, poses)
+    returns (image_xyz [B, nv, h, w, 3] f32, image_mask [B, nv, h, w] bool, knn_global [N, k] int64).
+    kinv: lifting.intrinsics_inverse(...) computed once for fixed intrinsics (no host work per step)."""
+    xyz32, mask, xyz64 = _lift.unproject_views_batched(cam_matrices, depths, poses, kinv=kinv)
     knn = _lift.knn_pixels_batched(xyz64, xyz32, mask, feat_aggre_points.reshape(-1, 3), lengths, k=k, global_ids=True)
     return xyz32, mask, knn
 

@@ -364,12 +364,21 @@ class GraphedTrainStep:
         self.replays = 0
 
     @staticmethod
-    def signature(pyr, features, labels):
+    def signature(pyr, features, labels, extras=None):
         sig = []
         for lst in (pyr.points, pyr.neighbors, pyr.pools, pyr.upsamples, pyr.lengths):
             sig.append(tuple((tuple(t.shape), str(t.dtype)) for t in lst))
         sig.append((tuple(features.shape), str(features.dtype), tuple(labels.shape), str(labels.dtype)))
+        for k in sorted(extras or {}):
+            sig.append((k, tuple(extras[k].shape), str(extras[k].dtype)))
         return tuple(sig)
+
+    @staticmethod
+    def _batch(pyr, features, labels, extras):
+        """The batch object the network consumes: the pyramid lists, `features` (KPFCNN) and any extra tensors by
+        name (the fusion nets read images / image_xyz / knn_global / feat_aggre_points / feature_3d)."""
+        return SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools, upsamples=pyr.upsamples,
+                               lengths=pyr.lengths, features=features, labels=labels, **(extras or {}))
 
     def _finish(self, grads=None):
         if self.reduce_grads is not None:
@@ -378,24 +387,31 @@ class GraphedTrainStep:
             torch.nn.utils.clip_grad_value_(self.params, self.grad_clip)  # utils/trainer.py:191-193
         self.opt.step()
 
-    def eager(self, pyr, features, labels):
-        batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools, upsamples=pyr.upsamples,
-                                lengths=pyr.lengths, features=features, labels=labels)
+    def eager(self, pyr, features, labels, extras=None):
+        batch = self._batch(pyr, features, labels, extras)
         loss = self.net.loss(self.net(batch), labels)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self._finish()
         return loss.detach()
 
-    def _capture(self, pyr, features, labels):
+    def _capture(self, pyr, features, labels, extras=None):
         from . import _lib
         clone = lambda lst: [t.clone() for t in lst]
-        static = SimpleNamespace(points=clone(pyr.points), neighbors=clone(pyr.neighbors), pools=clone(pyr.pools),
-                                 upsamples=clone(pyr.upsamples), lengths=clone(pyr.lengths), features=features.clone(),
-                                 labels=labels.clone())
+        spyr = SimpleNamespace(points=clone(pyr.points), neighbors=clone(pyr.neighbors), pools=clone(pyr.pools),
+                               upsamples=clone(pyr.upsamples), lengths=clone(pyr.lengths))
+        static = self._batch(spyr, features.clone(), labels.clone(), {k: v.clone() for k, v in (extras or {}).items()})
+        static.extras = sorted(extras or {})
         L = _lib.lib()
         entry = SimpleNamespace(static=static, graph_a=torch.cuda.CUDAGraph(), graph_b=None, loss=None, grads=None)
         self.opt.zero_grad(set_to_none=True)
+        # tensors a module keeps from the previous (eager) step -- the deformable layers' min_d2 / deformed_KP /
+        # offset_features that the regulariser reads -- hold that step's autograd graph alive, including the
+        # AccumulateGrad nodes of their parameters, which are bound to the stream of the eager step
+        for m in self.net.modules():
+            for attr in ("min_d2", "deformed_KP", "offset_features"):
+                if getattr(m, attr, None) is not None:
+                    setattr(m, attr, None)
         torch.cuda.synchronize()
         _lib._ZEROS.buf = None  # zero-initialised scratch must be allocated (and re-zeroed on replay) inside the graph
         l0 = L.mvk_launch_count()
@@ -417,18 +433,18 @@ class GraphedTrainStep:
         self.launches_per_step = int(L.mvk_launch_count() - l0)
         return entry
 
-    def __call__(self, pyr, features, labels):
-        """Runs one step on (pyramid, features, labels); returns the loss (a device scalar that the next call
-        overwrites -- read or copy it before)."""
+    def __call__(self, pyr, features, labels, extras=None):
+        """Runs one step on (pyramid, features, labels[, extra batch tensors by name]); returns the loss (a device
+        scalar that the next call overwrites -- read or copy it before)."""
         from . import _weights
-        sig = self.signature(pyr, features, labels)
+        sig = self.signature(pyr, features, labels, extras)
         entry = self.graphs.get(sig)
         if entry is None:
             n = self.seen.get(sig, 0)
             self.seen[sig] = n + 1
             if n < self.warm:
-                return self.eager(pyr, features, labels)
-            entry = self._capture(pyr, features, labels)  # records only; the static buffers hold this batch already
+                return self.eager(pyr, features, labels, extras)
+            entry = self._capture(pyr, features, labels, extras)  # records only; the static buffers hold this batch already
             self.graphs[sig] = entry
             while len(self.graphs) > self.max_graphs:
                 self.graphs.popitem(last=False)
@@ -440,6 +456,8 @@ class GraphedTrainStep:
                 torch._foreach_copy_(dst, src)
             st.features.copy_(features)
             st.labels.copy_(labels)
+            for k in st.extras:
+                getattr(st, k).copy_(extras[k])
         entry.graph_a.replay()
         if entry.graph_b is not None:
             self.reduce_grads(entry.grads)

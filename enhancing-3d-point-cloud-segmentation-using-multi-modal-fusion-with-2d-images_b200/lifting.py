@@ -312,7 +312,16 @@ def knn_pixels(xyz64, mask, queries, k=3):
 # Batched lifting: all spheres of a stacked batch at once (replaces the per-sphere loops of
 # ScanNet_sphere_color.py:409-452 and architectures_sphere.py:246-279)
 # -------------------------------------------------------------------------------------------------
-def unproject_views_batched(cam_matrices, depths, poses):
+def intrinsics_inverse(cam_matrices, B, nv, device):
+    """[B*nv, 9] f64 device tensor of inv(cam[:3,:3]) per view: inverted on the host in fp32 like the reference (one
+    3x3 per sphere, ScanNet_sphere_color.py:69), widened to fp64.  Reusable across steps for fixed intrinsics."""
+    cam = cam_matrices.detach().cpu().numpy() if isinstance(cam_matrices, torch.Tensor) else np.asarray(cam_matrices)
+    cam = np.broadcast_to(cam.reshape(-1, 4, 4) if cam.ndim == 3 else cam[None], (B, 4, 4))
+    kinv = np.stack([_kinv64(c) for c in cam], 0)
+    return torch.from_numpy(np.ascontiguousarray(np.repeat(kinv, nv, axis=0).reshape(B * nv, 9))).to(device)
+
+
+def unproject_views_batched(cam_matrices, depths, poses, kinv=None):
     """Every view of every sphere of a batch in one launch.
 
     cam_matrices (B, 4, 4) or (4, 4) float32 (already rescaled to the depth resolution, :370-372),
@@ -327,11 +336,8 @@ def unproject_views_batched(cam_matrices, depths, poses):
     dev = d.device
     P = poses if isinstance(poses, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(poses, dtype=np.float32))
     P = P.to(dev).contiguous().float().reshape(B * nv, 16)
-    cam = cam_matrices.detach().cpu().numpy() if isinstance(cam_matrices, torch.Tensor) else np.asarray(cam_matrices)
-    cam = np.broadcast_to(cam.reshape(-1, 4, 4) if cam.ndim == 3 else cam[None], (B, 4, 4))
-    # inv() on the host in fp32 like the reference (one 3x3 per sphere), widened to fp64, one copy per view
-    kinv = np.stack([_kinv64(c) for c in cam], 0)
-    kinv = torch.from_numpy(np.ascontiguousarray(np.repeat(kinv, nv, axis=0).reshape(B * nv, 9))).to(dev)
+    if kinv is None:
+        kinv = intrinsics_inverse(cam_matrices, B, nv, dev)
     xyz64 = torch.empty((B * nv * h * w, 3), dtype=torch.float64, device=dev)
     xyz32 = torch.empty((B, nv, h, w, 3), dtype=torch.float32, device=dev)
     mask = torch.empty((B, nv, h, w), dtype=torch.uint8, device=dev)

@@ -112,3 +112,22 @@ def make_views(points_world, n_views=3, h=120, w=160, seed=0, hole_frac=0.05):
         depths.append(depth.astype(np.float32))
         poses.append(pose)
     return cam, np.stack(depths), np.stack(poses)
+
+
+def make_fusion_spheres(n_spheres, subsample, seed=0, in_radius=2.0, first_dl=0.04, density=9000.0, n_views=3, h=120, w=160):
+    """Spheres with their RGB-D views (BASELINE configs[2-3]): like make_spheres, plus for every
+    sphere the world-frame points (the reference's feat_aggre_points), a depth-intrinsics matrix scaled to (w, h),
+    n_views depth maps rendered from the sphere's own points and the camera poses.  Returns a list of namespaces
+    (points centred [n,3], world [n,3], cam [4,4], depths [nv,h,w], poses [nv,4,4])."""
+    from types import SimpleNamespace
+    rng = np.random.default_rng(seed + 1000)
+    out = []
+    for i in range(n_spheres):
+        room = make_room(seed=seed + i, density=density)
+        sub = np.asarray(subsample(room, first_dl), dtype=np.float32)
+        c = np.array([rng.uniform(1.5, ROOM[0] - 1.5), rng.uniform(1.5, ROOM[1] - 1.5), 1.0], np.float32)
+        centred = crop_sphere(sub, c, in_radius)
+        world = (centred + c).astype(np.float32)
+        cam, depths, poses = make_views(world, n_views=n_views, h=h, w=w, seed=seed + i)
+        out.append(SimpleNamespace(points=centred, world=world, cam=cam, depths=depths, poses=poses))
+    return out

@@ -130,8 +130,10 @@ def lifting_cpu(cam, depths, poses, feature_2d, sphere_pts, conv_weights, iters=
         t2 = time.perf_counter()
         f2 = torch.from_numpy(np.ascontiguousarray(feature_2d.transpose(1, 0, 2, 3).reshape(1, c, -1))).requires_grad_(True)
         ii = torch.from_numpy(flat).long().unsqueeze(0)
-        src = modules.group_points(torch.from_numpy(np.ascontiguousarray(xyz.T.astype(np.float32))).unsqueeze(0), ii)
-        gf = modules.group_points(f2, ii)
+        # group_points as plain indexing (the expand + gather of the reference's test oracle would materialise a
+        # (C, np, nv*h*w) gradient in backward)
+        src = torch.from_numpy(np.ascontiguousarray(xyz.T.astype(np.float32)))[:, ii[0]].unsqueeze(0)
+        gf = f2[:, :, ii[0]]
         tgt = torch.from_numpy(np.ascontiguousarray(sphere_pts.T.astype(np.float32))).unsqueeze(0)
         out = modules.feature_aggregation_forward(src, tgt, gf, ws, bn_w, bn_b, None, None, training=True)
         out.sum().backward()

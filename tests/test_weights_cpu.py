@@ -58,13 +58,22 @@ def test_weight_registry_bookkeeping(mvk, monkeypatch):
     assert W._EPOCH[0] == epoch + 1
     W.weight_operands(b, *kb)
     assert calls[-1][0] == "multi" and len(calls) == 4
-    # a different view of the same parameter (other padding) re-registers on its own
+    # a different view of the same parameter (other padding) registers on its own, next to the first one
     W.weight_operands(b, 24, 16, 16, 32, 16)
     assert calls[-1][0] == "single"
+    # a reshaped VIEW of a parameter (a new tensor object on every call) maps to the entry of its base
+    c = torch.nn.Parameter(torch.randn(6, 4, 1, 1))
+    kc = (6, 4, 4, 6, 8)
+    W.weight_operands(c.reshape(6, 4), *kc)
+    n = len(calls)
+    assert calls[-1][0] == "single"
+    W.weight_operands(c.reshape(6, 4), *kc)
+    W.weight_operands(c.view(6, 4), *kc)
+    assert len(calls) == n                                   # same owner, same offset: nothing launched
     # dead parameters leave the table at the next refresh
-    del a, opt
+    del a, opt, c
     gc.collect()
     W.invalidate()
     W.weight_operands(b, 24, 16, 16, 32, 16)
-    assert calls[-1] == ("multi", 1, 1)
-    assert len(table.entries) == 1
+    assert calls[-1][0] == "multi" and calls[-1][1] == 2     # b's two operand layouts
+    assert len(table.entries) == 2
