@@ -822,7 +822,8 @@ bool tiny_ok(int cin, int num_kp, int influence, int aggregation) {
 }
 int fast_g(int cin) { return cin == 32 ? 8 : (cin == 64 ? 16 : 32); }
 
-int pick_v(int cin) { return (cin % 128 == 0) ? 4 : ((cin % 64 == 0) ? 2 : 1); }
+// channels per lane of the generic kernels: any width that keeps the 16 / 8-byte row alignment of x
+int pick_v(int cin) { return (cin % 4 == 0) ? 4 : ((cin % 2 == 0) ? 2 : 1); }
 
 }  // namespace
 }  // namespace mvk

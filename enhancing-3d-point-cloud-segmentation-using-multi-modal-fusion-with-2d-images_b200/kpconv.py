@@ -34,6 +34,9 @@ _AGGREGATION = {"sum": 0, "closest": 1}
 CONTRACTIONS = ("bf16x3", "bf16", "fp32")
 
 DEFAULT_CONTRACTION = os.environ.get("MVK_CONTRACTION", "bf16x3")
+# forward = ONE kernel (stage A + tcgen05 contraction, the weighted operand stays in shared memory) on the shapes
+# mvk_kpconv_fused supports; "0" keeps the two-kernel sequence everywhere (A/B timing, bisecting)
+FUSED_FORWARD = os.environ.get("MVK_FUSED", "1") != "0"
 
 
 def _round_up(a, b):
@@ -101,14 +104,25 @@ class _KPConvFunction(torch.autograd.Function):
                 terms = 3 if contraction == "bf16x3" else 1
                 ld = _round_up(kd, 8)      # 16-byte row pitch is all TMA needs: partial tiles are zero-filled
                 npad = _round_up(cout, 8)
-                keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld)
-                check(L.mvk_kpconv_weighted(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(), cin,
-                                            kp.data_ptr(), K, float(kp_extent), influence, aggregation, ld, None, a_hi,
-                                            a_lo, st))
                 w_hi, w_lo, wkeep, _ = _weights.weight_operands(w, kd, cout, cout, ld, npad)  # once per optimiser step
-                if nq > 0:
-                    check(L.mvk_gemm_bf16x3(a_hi, a_lo, 0, ld, w_hi, w_lo, 1, npad, nq, npad, ld, out.data_ptr(), cout,
-                                            cout, terms, 0, st))
+                # the weighted operand is only kept (written once, never re-read in forward) when a backward will
+                # contract it again for dW
+                need_a = bool(ctx.needs_input_grad[4])  # (all False under torch.no_grad(): inference keeps nothing)
+                fused = (FUSED_FORWARD and terms == 3 and nq > 0 and
+                         L.mvk_kpconv_fused_supported(cin, cout, K, h, influence, aggregation) == 1)
+                if fused:
+                    keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld if need_a else 0, 2 * nq * ld if need_a else 0)
+                    check(L.mvk_kpconv_fused(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(), cin,
+                                             kp.data_ptr(), K, float(kp_extent), cout, w_hi, w_lo, npad, out.data_ptr(),
+                                             a_hi, a_lo, ld, st))
+                else:
+                    keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld)
+                    check(L.mvk_kpconv_weighted(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(),
+                                                cin, kp.data_ptr(), K, float(kp_extent), influence, aggregation, ld, None,
+                                                a_hi, a_lo, st))
+                    if nq > 0:
+                        check(L.mvk_gemm_bf16x3(a_hi, a_lo, 0, ld, w_hi, w_lo, 1, npad, nq, npad, ld, out.data_ptr(), cout,
+                                                cout, terms, 0, st))
                 ptrs = (a_hi, a_lo, w_hi, w_lo)
         ctx.save_for_backward(q, s, inds, kp, w, keep)  # autograd's version check on w also guards its bf16 pair
         ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64, ld, npad, ptrs)

@@ -362,6 +362,22 @@ int mvk_fa_gather_views(const float* feat, long long view_stride, long long chan
                         int hw, const float* xyz32, const long long* knn_global, int np, int k, const float* tgt_xyz,
                         float* X, int ldx, mvk_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused KPConv forward (blocks.py:277-374, rigid / 'linear' / 'sum'): stage A + contraction in ONE kernel, the
+ * weighted operand [nq, K*cin] staying in shared memory ("0 if fused").
+ *   out [nq, cout] f32 = sum_k (sum_h w_ihk x[j_ih]) @ W[k]   with W given as its bf16 hi/lo pair [K*cin, ldw]
+ *   (rows k*cin + c, row pitch ldw elements; what mvk_split_bf16 writes), bf16x3 arithmetic on tcgen05.
+ *   a_hi / a_lo (both or neither; [nq, ld] bf16): when given, the weighted operand is ALSO written out once for
+ *   the backward pass (dW = A^T dOut); the forward never reads it back.
+ * Supported: cin in {32, 64, 128}, cout in {32, 64, 128}, num_kp <= 15, h <= 48 (mvk_kpconv_fused_supported);
+ * everything else returns MVK_ERR_UNSUPPORTED and the caller runs mvk_kpconv_weighted + mvk_gemm_bf16x3.
+ * ---------------------------------------------------------------------------------------------- */
+int mvk_kpconv_fused_supported(int cin, int cout, int num_kp, int h, int influence, int aggregation);
+int mvk_kpconv_fused(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                     int idx_is_i64, int h, const float* x, int cin, const float* kernel_points, int num_kp,
+                     float kp_extent, int cout, const void* w_hi, const void* w_lo, int ldw, float* out,
+                     void* a_hi, void* a_lo, int ld, mvk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
