@@ -36,6 +36,7 @@ constexpr int FT_ASTAGES = 2;
 constexpr int FT_A_TILE = 16384;          // 128 rows x 128 B (hi or lo)
 constexpr int FT_GEOM_BYTES = FT_M * FT_HCAP * 16;
 constexpr int FT_LIST_BYTES = FT_GW * 4 * FT_HCAP * 4;  // per warp: 4 lists x 48 packed entries
+constexpr int FT_NL = 8;                 // list entries gathered per trip
 constexpr int FT_STAGING = 16384;         // epilogue tile [128 rows x 32 fp32]
 
 struct FusedArgs {
@@ -265,23 +266,33 @@ kp_fused_fwd(const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant_
                     const unsigned int* lk = my_lists + sg * FT_HCAP;
                     const float4* gk = my_geom + (pp + pt_of_sg) * FT_HCAP;
                     const char* xb = (const char*)(a.x + ch_off + lg * 4);
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-                    for (int e = 0; e < n; e += 2) {
-                        const uint2 ee = *(const uint2*)(lk + e);
-                        const float w0 = (float)(ee.x & 0xffffffu) * (1.f / 16777216.f);
-                        const unsigned int o0 = __float_as_uint(gk[ee.x >> 24].w);
-                        const float4 x0 = __ldg((const float4*)(xb + o0));
-                        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float w1 = 0.f;
-                        if (e + 1 < n) {
-                            w1 = (float)(ee.y & 0xffffffu) * (1.f / 16777216.f);
-                            x1 = __ldg((const float4*)(xb + __float_as_uint(gk[ee.y >> 24].w)));
+                    // up to FT_NL gathers in flight per lane (a list holds ~4.5 entries on average): all loads are issued
+                    // before the first FMA, so one L2 round trip covers the whole list
+                    float w8[FT_NL];
+                    float4 x8[FT_NL];
+#pragma unroll
+                    for (int u = 0; u < FT_NL; u++) {
+                        w8[u] = 0.f;
+                        x8[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (u < n) {
+                            const unsigned int e = lk[u];
+                            w8[u] = (float)(e & 0xffffffu) * (1.f / 16777216.f);
+                            x8[u] = __ldg((const float4*)(xb + __float_as_uint(gk[e >> 24].w)));
                         }
-                        acc.x = fmaf(w0, x0.x, acc.x); acc.y = fmaf(w0, x0.y, acc.y);
-                        acc.z = fmaf(w0, x0.z, acc.z); acc.w = fmaf(w0, x0.w, acc.w);
-                        acc.x = fmaf(w1, x1.x, acc.x); acc.y = fmaf(w1, x1.y, acc.y);
-                        acc.z = fmaf(w1, x1.z, acc.z); acc.w = fmaf(w1, x1.w, acc.w);
+                    }
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < FT_NL; u++) {
+                        acc.x = fmaf(w8[u], x8[u].x, acc.x); acc.y = fmaf(w8[u], x8[u].y, acc.y);
+                        acc.z = fmaf(w8[u], x8[u].z, acc.z); acc.w = fmaf(w8[u], x8[u].w, acc.w);
+                    }
+#pragma unroll 1
+                    for (int u = FT_NL; u < n; u++) {  // long lists (rare)
+                        const unsigned int e = lk[u];
+                        const float w = (float)(e & 0xffffffu) * (1.f / 16777216.f);
+                        const float4 xv = __ldg((const float4*)(xb + __float_as_uint(gk[e >> 24].w)));
+                        acc.x = fmaf(w, xv.x, acc.x); acc.y = fmaf(w, xv.y, acc.y);
+                        acc.z = fmaf(w, xv.z, acc.z); acc.w = fmaf(w, xv.w, acc.w);
                     }
                     // bf16 hi / lo, 8 bytes each, into the swizzled K-major tile: row = point, column = position in the k-block
                     const __nv_bfloat162 h0 = __floats2bfloat162_rn(acc.x, acc.y), h1 = __floats2bfloat162_rn(acc.z, acc.w);

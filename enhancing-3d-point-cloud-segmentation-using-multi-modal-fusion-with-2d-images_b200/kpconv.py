@@ -34,9 +34,11 @@ _AGGREGATION = {"sum": 0, "closest": 1}
 CONTRACTIONS = ("bf16x3", "bf16", "fp32")
 
 DEFAULT_CONTRACTION = os.environ.get("MVK_CONTRACTION", "bf16x3")
-# forward = ONE kernel (stage A + tcgen05 contraction, the weighted operand stays in shared memory) on the shapes
-# mvk_kpconv_fused supports; "0" keeps the two-kernel sequence everywhere (A/B timing, bisecting)
-FUSED_FORWARD = os.environ.get("MVK_FUSED", "1") != "0"
+# MVK_FUSED=1: forward = ONE kernel (stage A + tcgen05 contraction, the weighted operand stays in shared memory) on the
+# shapes mvk_kpconv_fused supports.  Parity-tested, but measured SLOWER than the two-kernel sequence on B200 (level 0:
+# 868 vs 652 us; the K-outer gather re-derives the influences per 64-column block and executes 2.2x the instructions of
+# kp_fwd_fast, profiles/r2h_fused_summary.md), so it is opt-in.
+FUSED_FORWARD = os.environ.get("MVK_FUSED", "0") == "1"
 
 
 def _round_up(a, b):
