@@ -121,7 +121,11 @@ def make_batch(rank):
     import mvkpconv_b200 as mvk
     from mvkpconv_b200 import synthetic
     sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)
-    spheres = synthetic.make_spheres(SPHERES_PER_GPU, sub, seed=100 * rank, in_radius=IN_RADIUS, first_dl=FIRST_DL)
+    # weak scaling = the SAME amount of work on every GPU: every rank stacks the same 8 seeded spheres, rotated by its
+    # rank (another batch order, other labels), so that the N-GPU job is N copies of the 1-GPU workload and the
+    # efficiency the driver computes measures the communication, not a difference between the ranks' batches
+    spheres = synthetic.make_spheres(SPHERES_PER_GPU, sub, seed=0, in_radius=IN_RADIUS, first_dl=FIRST_DL)
+    spheres = spheres[rank % len(spheres):] + spheres[:rank % len(spheres)]
     pts_h, lens_h = synthetic.stack(spheres)
     feats_h = host_features(pts_h)
     labels_h = np.random.default_rng(rank).integers(0, 20, len(pts_h)).astype(np.int64)
@@ -206,8 +210,7 @@ def run_b200(args):
             return
         with dist._coalescing_manager(device=dev, async_ops=False):
             for g in grads:
-                dist.all_reduce(g)
-        torch._foreach_div_(grads, float(world))
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)  # the mean inside the collective: no separate division pass
 
     graphs_on = (not args.no_graphs) and not use_ddp and averager is None
     stepper = harness.GraphedTrainStep(net, opt, grad_clip=100.0,
@@ -569,8 +572,9 @@ def run_fusion(args, fusion, steps=None, warmup=None, emit=True):
     nv, h, w = FUSION_VIEWS[fusion], 120, 160
     L = _lib.lib()
     sub = lambda p, dl: mvk.grid_subsampling(p, sampleDl=dl)
-    sph = synthetic.make_fusion_spheres(SPHERES_PER_GPU, sub, seed=100 * rank, in_radius=IN_RADIUS, first_dl=FIRST_DL,
+    sph = synthetic.make_fusion_spheres(SPHERES_PER_GPU, sub, seed=0, in_radius=IN_RADIUS, first_dl=FIRST_DL,
                                         n_views=nv, h=h, w=w)
+    sph = sph[rank % len(sph):] + sph[:rank % len(sph)]  # same work on every rank (see make_batch)
     pts_h = np.concatenate([s.points for s in sph], 0)
     world_h = np.concatenate([s.world for s in sph], 0)
     lens_h = np.array([len(s.points) for s in sph], np.int32)
@@ -605,8 +609,7 @@ def run_fusion(args, fusion, steps=None, warmup=None, emit=True):
     def allreduce_grads(grads):
         with dist._coalescing_manager(device=dev, async_ops=False):
             for g in grads:
-                dist.all_reduce(g)
-        torch._foreach_div_(grads, float(world))
+                dist.all_reduce(g, op=dist.ReduceOp.AVG)
 
     graphs_on = not args.no_graphs
     stepper = harness.GraphedTrainStep(net, opt, grad_clip=100.0, reduce_grads=allreduce_grads if world > 1 else None,

@@ -106,6 +106,8 @@ def _norm_forward(L, y_ptr, ld, rows, cols, use_bn, training, gamma, beta, rm, r
     if not use_bn:
         return None, (beta.data_ptr() if beta is not None else None), None, None
     sc, sh, mu, isd = vec
+    if training and rows == 1:  # like nn.BatchNorm1d in the reference blocks (blocks.py:446-460)
+        raise ValueError("Expected more than 1 value per channel when training, got input size [1, %d]" % cols)
     if training and rows > 0 and stats is not None:
         # the column sums came out of the contraction's epilogue: only the [cols]-sized bookkeeping is left
         check(L.mvk_bn_finalize(stats, rows, cols, gamma.data_ptr(), beta.data_ptr(), eps, momentum, 1, ptr(rm), ptr(rv),

@@ -203,7 +203,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constan
         // (output-bound shapes) two warps share a lane quarter and take alternate 32-column chunks.
         const int quarter = warp & 3;
         const int nhalf = p.ew >> 2, half = (warp - 2) >> 2;
-        const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (uint32_t)STAGING_PER_WARP;
         // fused batch-norm statistics: warp-private column partials [2][256] behind the staging tiles
         float* colsum = (float*)(smem_dyn + (staging - smem_u32(smem_dyn)) + p.ew * STAGING_PER_WARP) + quarter * 512;
         const bool stats_on = p.col_stats != nullptr;
@@ -364,15 +363,7 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int a_mn_major, int lda
     p.kb_total = (K + BK - 1) / BK;
     // output-bound shapes (short reductions): 8 epilogue warps, tiles at most 128 wide
     p.ew = 4;
-    {
-        static const char* e_ew = getenv("MVK_GEMM_EW");
-        (void)e_ew;
-    }
-    p.bn = choose_bn(n_valid, p.b_mn != 0, p.ew == 8 ? 128 : 256);
-    {
-        static const char* e_bn = getenv("MVK_GEMM_BN");
-        if (e_bn && atoi(e_bn) >= 32 && (!p.b_mn || atoi(e_bn) >= 64)) p.bn = atoi(e_bn);
-    }
+    p.bn = choose_bn(n_valid, p.b_mn != 0, 256);
     p.kb_total = (K + BK - 1) / BK;
     bool auto_split = false;
     if (split_k == 0) {
@@ -411,14 +402,6 @@ static int gemm_impl(const void* a_hi, const void* a_lo, int a_mn_major, int lda
     p.tma_store = ((ldd % 4) == 0 && (((size_t)D) & 15) == 0) ? 1 : 0;
     // output row pitch not a multiple of 16 bytes: fragment-layout epilogue (8-byte sector-exact stores)
     if (!p.tma_store && (n_valid % 2) == 0 && (ldd % 2) == 0 && (((size_t)D) & 7) == 0) p.tma_store = 2;
-    {   // development overrides (scripts/gemm_bench.py)
-        static const char* e_store = getenv("MVK_GEMM_TMA_STORE");
-        if (e_store && e_store[0] == '2' && (n_valid % 2) == 0 && (ldd % 2) == 0) p.tma_store = 2;
-        if (e_store && e_store[0] == '1' && (ldd % 4) == 0) p.tma_store = 1;
-        static const char* e_stages = getenv("MVK_GEMM_STAGES");
-        if (e_store && e_store[0] == '0') p.tma_store = 0;
-        if (e_stages && atoi(e_stages) >= 1 && atoi(e_stages) < p.stages) p.stages = atoi(e_stages);
-    }
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, md;
     int rc;

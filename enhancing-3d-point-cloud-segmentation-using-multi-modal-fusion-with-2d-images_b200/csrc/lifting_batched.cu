@@ -313,7 +313,9 @@ kb_query(const float* __restrict__ q, int nq, int nb, int npix, int D, int k, in
 }
 
 // Exhaustive pass for the unresolved queries: one warp per query, lanes stride over the element's keys, the 32
-// per-lane top lists are merged by k rounds of a warp-wide lexicographic arg-min.
+// per-lane top lists are merged by k rounds of a warp-wide lexicographic arg-min.  (Measured alternative: growing
+// the ring search warp-cooperatively up to 16 rings before scanning -- 19 ms instead of 4 ms on the bench batch:
+// the shell walk is a chain of dependent, scattered cell reads, the scan streams the sorted keys.)
 template <int S>
 __global__ void __launch_bounds__(256)
 kb_far(const float* __restrict__ q, int nq, int nb, int npix, int D, int k, int global_ids, long long* __restrict__ out,

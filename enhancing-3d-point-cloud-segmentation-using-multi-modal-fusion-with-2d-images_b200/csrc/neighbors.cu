@@ -266,10 +266,7 @@ k_query(const float* __restrict__ q, int nq, int nb, float r2, double inv_cell, 
     }
 }
 
-int flat_cap() {  // development switch: MVK_NB_FLAT=0 restores the lane-per-cell candidate walk
-    static const char* e = getenv("MVK_NB_FLAT");
-    return (e && e[0] == '0') ? -1 : CAND_CAP;
-}
+int flat_cap() { return CAND_CAP; }
 
 int build(const float* s, int ns, const int* ql, const int* sl, int nb, float radius, Grid& g,
           cudaStream_t st) {

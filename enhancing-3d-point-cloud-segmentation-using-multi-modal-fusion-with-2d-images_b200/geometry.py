@@ -68,15 +68,13 @@ def create_3D_rotations(axis, angle):
 # -------------------------------------------------------------------------------------------------
 def batch_neighbors(queries, supports, q_batches, s_batches, radius, max_neighbors=None,
                     out_dtype=torch.int32, return_counts=False, deferred=None):
-    """Computes neighbors for a batch of queries and supports (datasets/common.py:185-196).
+    """Radius neighbours inside every element of a stacked batch; drop-in for the wrapper at
+    datasets/common.py:185-196 (same argument order).
 
-    :param queries: (N1, 3) the query points
-    :param supports: (N2, 3) the support points
-    :param q_batches: (B) the list of lengths of batch elements in queries
-    :param s_batches: (B) the list of lengths of batch elements in supports
-    :param radius: float32
-    :return: neighbors indices, int32 (N1, max_count): stacked support indices sorted by
-             (distance, index), padded with N2.
+    queries [N1, 3] and supports [N2, 3] are stacked clouds, q_batches / s_batches [B] give the number of points
+    of each element, radius is rounded to float32 like the C extension does.  Returns int32 [N1, max_count]:
+    for every query the stacked indices of its element's supports closer than radius, nearest first (ties by
+    index), rows filled up with N2.
 
     Extras (not in the reference signature, defaults keep its behaviour): `max_neighbors` crops
     the rows to their nearest entries on the device (== big_neighborhood_filter,

@@ -242,14 +242,16 @@ class KPFCNN(nn.Module):
         for m in self.kpconv_layers():
             if not getattr(m, "deformable", False):
                 continue
-            d2 = m.min_d2 / (m.KP_extent ** 2)
-            fitting = fitting + self.l1(d2, torch.zeros_like(d2))
-            locs = m.deformed_KP / m.KP_extent
-            for i in range(self.K):
-                other = torch.cat([locs[:, :i, :], locs[:, i + 1:, :]], dim=1).detach()
-                dist = torch.sqrt(torch.sum((other - locs[:, i:i + 1, :]) ** 2, dim=2))
-                rep = torch.sum(torch.clamp_max(dist - self.repulse_extent, max=0.0) ** 2, dim=1)
-                repulsive = repulsive + self.l1(rep, torch.zeros_like(rep)) / self.K
+            # fitting: mean over (point, kernel point) of the squared distance to the closest input point
+            fitting = fitting + (m.min_d2 / (m.KP_extent ** 2)).abs().mean()
+            # repulsion: all kernel-point pairs of a neighbourhood at once; pair (i, j) pushes point i away from a
+            # DETACHED point j (architectures.py:41-48), the self pair (distance 0, hinge repulse_extent^2) is masked
+            locs = m.deformed_KP / m.KP_extent                                   # [N, K, 3]
+            diff = locs.unsqueeze(2) - locs.detach().unsqueeze(1)                # [N, K (i), K (j), 3]
+            dist = torch.sqrt((diff * diff).sum(-1) + torch.eye(self.K, device=locs.device, dtype=locs.dtype))
+            hinge = torch.clamp_max(dist - self.repulse_extent, max=0.0) ** 2
+            hinge = hinge * (1.0 - torch.eye(self.K, device=locs.device, dtype=locs.dtype))
+            repulsive = repulsive + hinge.sum(2).mean(0).sum() / self.K  # sum_i mean_n sum_{j != i} hinge / K
         return self.deform_fitting_power * (2 * fitting + repulsive)
 
     def kpconv_layers(self):

@@ -308,20 +308,19 @@ class KPConv(nn.Module):
     def __init__(self, kernel_size, p_dim, in_channels, out_channels, KP_extent, radius,
                  fixed_kernel_points='center', KP_influence='linear', aggregation_mode='sum',
                  deformable=False, modulated=False, contraction=None):
-        """
-        Initialize parameters for KPConv (same arguments as blocks.py:145-147).
-        :param kernel_size: Number of kernel points.
-        :param p_dim: dimension of the point space.
-        :param in_channels: dimension of input features.
-        :param out_channels: dimension of output features.
-        :param KP_extent: influence radius of each kernel point.
-        :param radius: radius used for kernel point init.
-        :param fixed_kernel_points: fix position of certain kernel points ('none', 'center' or 'verticals').
-        :param KP_influence: influence function of the kernel points ('constant', 'linear', 'gaussian').
-        :param aggregation_mode: choose to sum influences, or only keep the closest ('closest', 'sum').
-        :param deformable: choose deformable or not
-        :param modulated: choose if kernel weights are modulated in addition to deformed
-        :param contraction: (extension) 'bf16x3' | 'bf16' | 'fp32'; default env MVK_CONTRACTION or 'bf16x3'
+        """Same positional arguments and defaults as the reference constructor (blocks.py:145-147):
+
+        kernel_size          K, how many kernel points carry a weight matrix
+        p_dim                dimension of the point coordinates (3 here)
+        in_channels / out_channels   feature widths Cin / Cout
+        KP_extent            reach of one kernel point's influence
+        radius               scale used to lay out the kernel points
+        fixed_kernel_points  which kernel points stay put during the layout ('none' | 'center' | 'verticals')
+        KP_influence         shape of the influence ('constant' | 'linear' | 'gaussian')
+        aggregation_mode     'sum' of all influences or only the 'closest' kernel point
+        deformable           learn per-point kernel offsets with an inner rigid KPConv
+        modulated            additionally learn a per-kernel-point modulation (deformable only)
+        contraction          (extension) 'bf16x3' | 'bf16' | 'fp32'; default: env MVK_CONTRACTION or 'bf16x3'
         """
         super(KPConv, self).__init__()
         # NB like the reference, `modulated` is simply ignored by a rigid layer (blocks.py:186-191):

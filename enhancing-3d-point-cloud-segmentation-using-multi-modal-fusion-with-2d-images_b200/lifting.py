@@ -53,14 +53,9 @@ class GroupPointsFunction(torch.autograd.Function):
 
 
 def group_points(points, index):
-    """Gather points by index
+    """out[b, c, n, k] = points[b, c, index[b, n, k]]  (mvpnet/ops/group_points.py:5-31).
 
-    Args:
-        points (torch.Tensor): (batch_size, channels, num_points)
-        index (torch.Tensor): (batch_size, num_centroids, num_neighbors), indices of neighbors of each centroid.
-
-    Returns:
-        group_points (torch.Tensor): (batch_size, channels, num_centroids, num_neighbors), grouped points.
+    points (B, C, N1) float32, index (B, N2, K) int64 -> (B, C, N2, K); differentiable w.r.t. points.
     """
     return GroupPointsFunction.apply(points, index)
 

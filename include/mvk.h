@@ -159,6 +159,8 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
  * Neighbours out of range of every kernel point are dropped like the reference's compaction
  * (:300-325).  Backward: grad_x (+=, caller zeroes; may be NULL), grad_kp [nq, K, 3] and grad_mod
  * [nq, K] (written; may be NULL); grad_min_d2 (may be NULL) is routed to grad_kp through argmin. */
+/* Deformable stage A supports num_kp <= 16 kernel points (one lane per kernel point holds its min_d2 / argmin; the
+ * reference scripts use 15) and rows up to ~530 neighbours wide (shared-memory lists, warps per CTA adapt). */
 int mvk_kpconv_deform_weighted(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                                int idx_is_i64, int h, const float* x, int cin, const float* deformed_kp,
                                const float* modulations, int num_kp, float kp_extent, int influence, int aggregation,

@@ -79,6 +79,42 @@ def test_neighbors_host_c_abi_entry(mvk):
     assert np.array_equal(arr.reshape(len(pts), width.value), geom.batch_neighbors(pts, pts, lens, lens, 0.1))
 
 
+def test_grid_subsample_host_c_abi_entry(mvk):
+    """mvk_grid_subsample_host: host buffers in, malloc'ed host buffers out (the entry point a maintainer of the
+    reference's cpp_subsampling wrapper would bind) -- points, features, labels and lengths
+    against the reference goldens (max_p crop included)."""
+    import ctypes as C
+    L = mvk._lib.lib()
+    g = load_golden("geometry")
+    pts = np.ascontiguousarray(g["points"], np.float32)
+    feats = np.ascontiguousarray(g["features"], np.float32).reshape(len(pts), -1)
+    labs = np.ascontiguousarray(g["labels"], np.int32).reshape(len(pts), -1)
+    lens = np.ascontiguousarray(g["lengths"], np.int32)
+    op, of, ol = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    olen = np.zeros(len(lens), np.int32)
+    tot = C.c_int()
+    rc = L.mvk_grid_subsample_host(pts.ctypes.data, len(pts), feats.ctypes.data, feats.shape[1], labs.ctypes.data,
+                                   labs.shape[1], lens.ctypes.data, len(lens), 0.2, 150, C.byref(op), C.byref(of),
+                                   C.byref(ol), olen.ctypes.data, C.byref(tot))
+    assert rc == 0
+    m = tot.value
+    take = lambda p, ct, shape: np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(int(np.prod(shape)),)).copy().reshape(shape)
+    sp, sf, sl = take(op, C.c_float, (m, 3)), take(of, C.c_float, (m, feats.shape[1])), take(ol, C.c_int, (m, labs.shape[1]))
+    for p in (op, of, ol):
+        L.mvk_free_host(p)
+    assert np.array_equal(sp, g["sub2_pts"]) and np.array_equal(olen, g["sub2_len"])
+    assert np.array_equal(sf.reshape(g["sub2_feats"].shape), g["sub2_feats"])
+    assert np.array_equal(sl.reshape(g["sub2_labels"].shape), g["sub2_labels"])
+    # points only (NULL features / labels), no crop
+    op = C.c_void_p()
+    rc = L.mvk_grid_subsample_host(pts.ctypes.data, len(pts), None, 0, None, 0, lens.ctypes.data, len(lens), 0.12, 0,
+                                   C.byref(op), None, None, olen.ctypes.data, C.byref(tot))
+    assert rc == 0
+    sp = take(op, C.c_float, (tot.value, 3))
+    L.mvk_free_host(op)
+    assert np.array_equal(sp, g["sub_pts"]) and np.array_equal(olen, g["sub_len"])
+
+
 def test_subsampling_vs_reference_golden(mvk):
     g = load_golden("geometry")
     sp, sl = mvk.batch_grid_subsampling(g["points"], g["lengths"], sampleDl=0.12, random_grid_orient=False)

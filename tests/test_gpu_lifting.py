@@ -123,34 +123,45 @@ def test_feature_aggregation_training_gradients_vs_oracle(mvk, contraction):
     tgt = torch.randn(b, 3, np_)
     feat = torch.randn(b, c, np_, k)
     go = torch.randn(b, 64, np_)
-    # oracle
-    fo = feat.clone().requires_grad_(True)
-    ws = [l.conv.weight.detach().cpu().clone().requires_grad_(True) for l in fa.mlp]
-    gs = [l.bn.weight.detach().cpu().clone().requires_grad_(True) for l in fa.mlp]
-    bs = [l.bn.bias.detach().cpu().clone().requires_grad_(True) for l in fa.mlp]
-    ref = modules.feature_aggregation_forward(src, tgt, fo, ws, gs, bs, None, None, True, "sum")
-    ref.backward(go)
+    # oracle in fp64 (the checker) and in fp32 (how far plain fp32 arithmetic itself sits from the fp64 result:
+    # the floor any fp32 implementation is entitled to, ReLU mask flips of near-zero pre-activations included)
+    def oracle(dt):
+        fo = feat.detach().clone().to(dt).requires_grad_(True)
+        ws = [l.conv.weight.detach().cpu().to(dt).requires_grad_(True) for l in fa.mlp]
+        gs = [l.bn.weight.detach().cpu().to(dt).requires_grad_(True) for l in fa.mlp]
+        bs = [l.bn.bias.detach().cpu().to(dt).requires_grad_(True) for l in fa.mlp]
+        ref = modules.feature_aggregation_forward(src.to(dt), tgt.to(dt), fo, ws, gs, bs, None, None, True, "sum")
+        ref.backward(go.to(dt))
+        named = {"out": ref.detach(), "grad_feature": fo.grad}
+        for i in range(len(ws)):
+            named[f"conv{i}.weight.grad"], named[f"bn{i}.weight.grad"], named[f"bn{i}.bias.grad"] = ws[i].grad, gs[i].grad, bs[i].grad
+        return named
+    ref64, ref32 = oracle(torch.float64), oracle(torch.float32)
     # product
     fg = feat.cuda().requires_grad_(True)
     out = fa(src.cuda(), tgt.cuda(), fg)
     out.backward(go.cuda())
-    tol = 2e-4
-    assert rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < tol
-    # element-wise gradients: a ReLU whose pre-activation is within rounding of zero flips its mask, which
-    # changes isolated entries by O(1); compare the tensor as a whole and bound the number of outliers
-    # (measured: typical entries agree to 2e-5; a handful of flips per 1.7 M activations with the bf16x3
-    # contraction, none expected with the strict fp32 one)
-    ga, gb = fg.grad.cpu().numpy().astype(np.float64), fo.grad.numpy().astype(np.float64)
-    strict = contraction == "fp32"
-    assert np.linalg.norm(ga - gb) / np.linalg.norm(gb) < (2e-3 if strict else 3e-2)
-    assert (np.abs(ga - gb) > tol * np.abs(gb).max()).mean() < (1e-4 if strict else 2e-3)
-    # a flipped mask changes a weight gradient (a sum of ~N random-sign terms) by ~1/sqrt(N) of its size
-    ptol = 5 * tol if strict else 5e-2
+    got = {"out": out.detach(), "grad_feature": fg.grad}
     for i, l in enumerate(fa.mlp):
-        assert rel_err(l.conv.weight.grad.cpu().numpy(), ws[i].grad.numpy()) < ptol, i
-        assert rel_err(l.bn.weight.grad.cpu().numpy(), gs[i].grad.numpy()) < ptol, i
-        assert rel_err(l.bn.bias.grad.cpu().numpy(), bs[i].grad.numpy()) < ptol, i
+        got[f"conv{i}.weight.grad"], got[f"bn{i}.weight.grad"], got[f"bn{i}.bias.grad"] = l.conv.weight.grad, l.bn.weight.grad, l.bn.bias.grad
         assert int(l.bn.num_batches_tracked) == 1
+    strict = contraction == "fp32"
+    worst = 0.0
+    for name, r64 in ref64.items():
+        e_gpu = rel_err(got[name].detach().cpu().numpy().reshape(r64.shape), r64.numpy())
+        e_f32 = rel_err(ref32[name].numpy(), r64.numpy())
+        print(f"FeatureAggregation[{contraction}] {name:20s} gpu vs fp64 {e_gpu:.2e}   host fp32 vs fp64 {e_f32:.2e}")
+        worst = max(worst, e_gpu)
+        # north_star: 1e-4 relative.  fp32 arithmetic itself is allowed its own distance from the fp64 result
+        # (a flipped ReLU mask moves isolated gradient entries by O(1)); bf16x3 is stated separately.
+        bar = max(1e-4, 4 * e_f32) if strict else max(1e-3, 20 * e_f32)
+        if name == "grad_feature" and not strict:
+            ga, gb = got[name].cpu().numpy().astype(np.float64), r64.numpy()
+            assert np.linalg.norm(ga - gb) / np.linalg.norm(gb) < 3e-2
+            assert (np.abs(ga - gb) > 2e-4 * np.abs(gb).max()).mean() < 2e-3
+            continue
+        assert e_gpu < bar, (name, e_gpu, e_f32, bar)
+    print(f"FeatureAggregation[{contraction}] worst tensor error vs fp64 oracle: {worst:.2e}")
     # the fused map entry point follows the same path when the module is being trained
     torch.manual_seed(5)
     npix = 3 * 19200
