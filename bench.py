@@ -203,7 +203,7 @@ def run_b200(args):
     def allreduce_grads(grads):
         """Gradient averaging right after backward, without DDP's buckets and per-parameter hooks: ONE grouped NCCL
         all-reduce over the per-parameter gradient tensors ('coalesced'), or one all-reduce of a packed copy ('flat')."""
-        if args.allreduce == "flat":
+        if len(grads) > 1 and args.allreduce == "flat":  # eager steps of the flat mode: pack, reduce, unpack
             flat = torch.cat([g.reshape(-1) for g in grads])
             dist.all_reduce(flat, op=dist.ReduceOp.AVG)
             torch._foreach_copy_(grads, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in grads]), grads)])
@@ -215,7 +215,7 @@ def run_b200(args):
     graphs_on = (not args.no_graphs) and not use_ddp and averager is None
     stepper = harness.GraphedTrainStep(net, opt, grad_clip=100.0,
                                        reduce_grads=allreduce_grads if (world > 1 and not use_ddp and averager is None) else None,
-                                       warm=2 if graphs_on else 10 ** 9)
+                                       warm=2 if graphs_on else 10 ** 9, flat_grads=args.allreduce != "coalesced")
     queries_per_step = [0]
     host_enqueue_ms = [0.0]
     per_rank = []
@@ -1067,7 +1067,7 @@ def main():
     ap.add_argument("--precision-2d", default="fp32", choices=["fp32", "bf16"], help="autocast of the frozen 2D network")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the config0 / neighbours / fp32-contraction legs of the N = 1 line")
-    ap.add_argument("--allreduce", default="coalesced", choices=["coalesced", "overlap", "flat", "ddp"],
+    ap.add_argument("--allreduce", default="flat", choices=["coalesced", "overlap", "flat", "ddp"],
                     help="N > 1: gradients packed into one buffer + ONE NCCL all-reduce (flat), a grouped all-reduce of the "
                          "per-parameter tensors (coalesced), or torch DDP buckets (ddp)")
     ap.add_argument("--detail", type=int, default=0, help="add the N most expensive (entry point, shape) rows")
