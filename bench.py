@@ -288,12 +288,16 @@ def run_b200(args):
             if prefetch._pending is not None:
                 prefetch.take()  # left over from the previous timed region (other input source)
             prefetch.submit(lambda: load_inputs(from_host))
+        # one clock sampler per job, on rank 0; started BEFORE the warm-up steps: nvidia-smi's own start-up (driver
+        # queries, ~100 ms) must not land inside the timed region (seen as 16-18 ms/step outliers in 20-step runs)
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if sampler is not None:
+            time.sleep(0.3)
         run_steps(from_host, warmup, st)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None  # one sampler per job, on rank 0
         l0, r0 = L.mvk_launch_count(), st.replays
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -659,6 +663,9 @@ def run_fusion(args, fusion, steps=None, warmup=None, emit=True):
     for _ in range(3):  # set-up: eager warm steps + capture
         one_step(False)
     sampler = ClockSampler(local) if (emit and rank == 0) else None
+    if sampler is not None:
+        time.sleep(0.3)  # nvidia-smi start-up outside the timed region
+        one_step(False)
     ms, launches, loss_v = timed(False, steps, warmup)
     clocks = sampler.stop() if sampler else None
     ms_e2e, _, _ = timed(True, steps, max(1, warmup // 2))

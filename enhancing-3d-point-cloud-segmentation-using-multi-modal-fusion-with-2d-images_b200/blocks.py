@@ -28,6 +28,8 @@ from . import kpconv as _kp
 
 
 _FUSE_BN_STATS = os.environ.get("MVK_FUSE_BN_STATS", "0") == "1"
+# decoder step: contract the upsampled half at the coarse level (_UpAddLinearBNAct); "0" = concatenated operand
+_DECODER_SPLIT = os.environ.get("MVK_DECODER_SPLIT", "1") != "0"
 
 
 def _r8(v):
@@ -377,6 +379,135 @@ class _UpCatLinearBNAct(torch.autograd.Function):
         return dcoarse, dw, dgamma, dbeta, dskip, None, None, None, None, None, None, None, None, None, None, None
 
 
+class _UpAddLinearBNAct(torch.autograd.Function):
+    """The decoder step of KPFCNN (architectures.py:300-306 + blocks.py:493-498),
+        z = leaky(bn(cat([closest_pool(x_coarse, inds), skip], 1) W^T)),
+    with the upsampled half contracted at the COARSE level: a Linear commutes with a row gather, so
+        cat([up(x), skip]) W^T = up(x W_up^T) + skip W_skip^T .
+    The fine-level contraction then runs over the skip channels only (at level 0 of the baseline net: 128 of 384
+    columns, 137 MB instead of 410 MB of operand per pass), the coarse one over 4.6x fewer rows, and
+    mvk_gather_add_rows adds the gathered coarse result.  Backward mirrors it: dskip = dy W_skip at the fine level,
+    d(x W_up^T) = closest_pool^T(dy) scattered to the coarse rows, dx_coarse / dW_up contracted there.
+    Argument positions 0 / 1 / 4 mirror _LinearBNAct (x, weight, residual)."""
+
+    @staticmethod
+    def forward(ctx, x_coarse, weight, gamma, beta, skip, rm, rv, use_bn, training, momentum, eps, slope, contraction,
+                nbt, emit_hilo, inds):
+        _lib.require_cuda()
+        L = _lib.lib()
+        if contraction == "fp32":
+            raise RuntimeError("the split decoder step needs a tensor-core contraction ('bf16x3' or 'bf16')")
+        xc, sk, w = _f32c(x_coarse), _f32c(skip), _f32c(weight)
+        ii, is64 = _kp._idx(inds if inds.dim() == 2 else inds.reshape(-1, 1))
+        ns, c1 = xc.shape
+        nq, c2 = sk.shape
+        cout, cin = w.shape
+        if ii.shape[0] != nq or cin != c1 + c2 or c1 % 8 or c2 % 8 or cout % 4:
+            raise RuntimeError("split decoder step: channel counts must be multiples of 8 (outputs: of 4)")
+        dev = xc.device
+        st = stream_ptr()
+        terms = 3 if contraction == "bf16x3" else 1
+        emit = bool(emit_hilo) and cout % 8 == 0
+        cc, cs = _cached_hilo(x_coarse, ns, c1), _cached_hilo(skip, nq, c2)
+        with _lib.on_device(dev):
+            keep, (xc_hi, xc_lo, sk_hi, sk_lo, zc, y, sc, sh, mu, isd, z_hi, z_lo) = _carve(
+                dev, *([0, 0] if cc is not None else [2 * ns * c1] * 2), *([0, 0] if cs is not None else [2 * nq * c2] * 2),
+                4 * ns * cout, 4 * nq * cout, *([4 * cout] * 4 if use_bn else [0] * 4),
+                *([2 * nq * cout] * 2 if emit else [0, 0]))
+            ckeep = skeep = None
+            if cc is not None:
+                xc_hi, xc_lo, ckeep = cc.hi, cc.lo, cc.keep
+            elif ns > 0:
+                check(L.mvk_split_bf16(xc.data_ptr(), ns, c1, c1, xc_hi, xc_lo, ns, c1, st))
+            if cs is not None:
+                sk_hi, sk_lo, skeep = cs.hi, cs.lo, cs.keep
+            elif nq > 0:
+                check(L.mvk_split_bf16(sk.data_ptr(), nq, c2, c2, sk_hi, sk_lo, nq, c2, st))
+            w_hi, w_lo, wkeep, _ = _weights.weight_operands(w, cout, cin, cin, cout, cin)  # [cout, c1 + c2], K-major
+            if nq > 0:
+                # fine level: skip W_skip^T  (B = columns c1.. of W: same row pitch, pointer moved by c1 elements)
+                check(L.mvk_gemm_bf16x3(sk_hi, sk_lo, 0, c2, w_hi + 2 * c1, w_lo + 2 * c1, 0, cin, nq, cout, c2, y, cout, cout,
+                                        terms, 0, st))
+                if ns > 0:
+                    # coarse level: x W_up^T, then gathered onto the fine rows
+                    check(L.mvk_gemm_bf16x3(xc_hi, xc_lo, 0, c1, w_hi, w_lo, 0, cin, ns, cout, c1, zc, cout, cout, terms, 0, st))
+                    check(L.mvk_gather_add_rows(y, cout, nq, cout, zc, ns, ii.data_ptr(), is64, ii.shape[1], st))
+            sc, sh, mu, isd = _norm_forward(L, y, cout, nq, cout, use_bn, training, gamma, beta, rm, rv, momentum, eps, st,
+                                            nbt, (sc, sh, mu, isd), dev, None)
+            z = torch.empty((nq, cout), dtype=torch.float32, device=dev)
+            check(L.mvk_scale_shift_act(y, nq, cout, cout, sc, sh, None, cout, slope, z.data_ptr(), cout, z_hi, z_lo, cout, st))
+        ctx.save_for_backward(keep, ckeep, skeep, w, ii, beta if not use_bn else None)
+        ctx.cfg = (ns, nq, c1, c2, cout, use_bn, training, slope, gamma is not None, beta is not None, terms, is64,
+                   (xc_hi, xc_lo, sk_hi, sk_lo, w_hi, w_lo, y, sc, sh, mu, isd), wkeep)
+        if emit:
+            _attach_hilo(z, keep, z_hi, z_lo, nq, cout)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        L = _lib.lib()
+        keep, ckeep, skeep, w, ii, _bias = ctx.saved_tensors
+        ns, nq, c1, c2, cout, use_bn, training, slope, has_g, has_b, terms, is64, ptrs, _wkeep = ctx.cfg
+        xc_hi, xc_lo, sk_hi, sk_lo, w_hi, w_lo, y, sc, sh, mu, isd = ptrs
+        cin = c1 + c2
+        need_c, need_w, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[4]
+        g, ldg = _rows_f32(dz)
+        dev = g.device
+        st = stream_ptr()
+        batch_stats = 1 if (use_bn and training) else 0
+        dcoarse = dw = dskip = None
+        with _lib.on_device(dev):
+            sums = _lib.zeros_ptr(16 * cout, dev)
+            if has_g or has_b or batch_stats:
+                check(L.mvk_act_bwd_reduce(g.data_ptr(), ldg, y, nq, cout, cout, sc, sh, None, cout, mu, isd, slope, sums, st))
+            dgamma = torch.empty(cout, dtype=torch.float32, device=dev) if has_g else None
+            dbeta = torch.empty(cout, dtype=torch.float32, device=dev) if has_b else None
+            coarse = (need_c or need_w) and ns > 0
+            ldh = _r8(cout)
+            dkeep, (dy_hi, dy_lo, dy32, dzc, dzc_hi, dzc_lo) = _carve(
+                dev, 2 * nq * ldh, 2 * nq * ldh, 4 * nq * cout if coarse else 0, 4 * ns * cout if coarse else 0,
+                2 * ns * ldh if coarse else 0, 2 * ns * ldh if coarse else 0)
+            check(L.mvk_act_bwd_apply(g.data_ptr(), ldg, y, nq, cout, cout, sc, sh, None, cout, mu, isd, slope, sums,
+                                      batch_stats, dy32, cout, dy_hi, dy_lo, ldh, None, cout, ptr(dgamma), ptr(dbeta), st))
+            if need_s:
+                dskip = torch.empty((nq, c2), dtype=torch.float32, device=dev)
+                if nq > 0:  # dskip = dy W_skip : B = W stored [K = cout, N = cin], columns c1.. (N contiguous)
+                    check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 0, ldh, w_hi + 2 * c1, w_lo + 2 * c1, 1, cin, nq, c2, cout,
+                                            dskip.data_ptr(), c2, c2, terms, 0, st))
+            if coarse:
+                # gradient of the gathered coarse result: every fine row adds its dy row to its coarse parent
+                _zero_region(dkeep, dzc, 4 * ns * cout)
+                if nq > 0:
+                    check(L.mvk_pool_bwd(dy32, cout, nq, cout, None, ii.data_ptr(), is64, ii.shape[1], 1, ns, dzc, st))
+                check(L.mvk_split_bf16(dzc, ns, cout, cout, dzc_hi, dzc_lo, ns, ldh, st))
+                if need_c:
+                    dcoarse = torch.empty((ns, c1), dtype=torch.float32, device=dev)
+                    check(L.mvk_gemm_bf16x3(dzc_hi, dzc_lo, 0, ldh, w_hi, w_lo, 1, cin, ns, c1, cout, dcoarse.data_ptr(), c1, c1,
+                                            terms, 0, st))
+            elif need_c:
+                dcoarse = torch.zeros((ns, c1), dtype=torch.float32, device=dev)
+            if need_w:
+                dw = torch.empty((cout, cin), dtype=torch.float32, device=dev)
+                if coarse:  # dW_up = (d(x W_up^T))^T x_coarse, contracted over the coarse rows
+                    check(L.mvk_gemm_bf16x3(dzc_hi, dzc_lo, 1, ldh, xc_hi, xc_lo, 1, c1, cout, c1, ns, dw.data_ptr(), cin, c1,
+                                            terms, 0, st))
+                else:
+                    dw[:, :c1].zero_()
+                if nq > 0:  # dW_skip = dy^T skip
+                    check(L.mvk_gemm_bf16x3(dy_hi, dy_lo, 1, ldh, sk_hi, sk_lo, 1, c2, cout, c2, nq, dw.data_ptr() + 4 * c1, cin,
+                                            c2, terms, 0, st))
+                else:
+                    dw[:, c1:].zero_()
+        return dcoarse, dw, dgamma, dbeta, dskip, None, None, None, None, None, None, None, None, None, None, None
+
+
+def _zero_region(keep, ptr_, nbytes):
+    """Zero `nbytes` of the carved allocation `keep` starting at device pointer `ptr_` (on the current stream)."""
+    if nbytes:
+        off = ptr_ - keep.data_ptr()
+        keep[off:off + nbytes].zero_()
+
+
 # -------------------------------------------------------------------------------------------------
 class BatchNormBlock(nn.Module):
 
@@ -454,8 +585,10 @@ class UnaryBlock(nn.Module):
             return self.forward(torch.cat([_kp.closest_pool(x_coarse, up_inds), skip], dim=1), emit_hilo=emit_hilo)
         slope = 1.0 if self.no_relu else 0.1
         use_bn, gamma, beta, rm, rv, momentum, eps, training, mod = _bn_args(self.batch_norm)
-        return _UpCatLinearBNAct.apply(x_coarse, self.mlp.weight, gamma, beta, skip, rm, rv, use_bn, training, momentum,
-                                       eps, float(slope), self.contraction, _nbt(mod, skip.shape[0]), emit_hilo, up_inds)
+        split = _DECODER_SPLIT and x_coarse.shape[1] % 8 == 0 and skip.shape[1] % 8 == 0 and self.out_dim % 4 == 0
+        fn = _UpAddLinearBNAct if split else _UpCatLinearBNAct
+        return fn.apply(x_coarse, self.mlp.weight, gamma, beta, skip, rm, rv, use_bn, training, momentum,
+                        eps, float(slope), self.contraction, _nbt(mod, skip.shape[0]), emit_hilo, up_inds)
 
     def __repr__(self):
         return 'UnaryBlock(in_feat: {:d}, out_feat: {:d}, BN: {:s}, ReLU: {:s})'.format(self.in_dim, self.out_dim,

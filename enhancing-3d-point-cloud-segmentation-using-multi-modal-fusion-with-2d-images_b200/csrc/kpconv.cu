@@ -832,6 +832,25 @@ kp_bwd_fast(KpArgs a, const float* __restrict__ gw, float* __restrict__ gx) {
     (void)kd;
 }
 
+// y[r, :] += z[inds[r, 0], :]  (rows whose first index is the shadow index keep y): the upsampled half of the decoder
+// Linear, contracted at the COARSE level and gathered here -- cat([up(x), skip]) W^T = up(x W_up^T) + skip W_skip^T.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather_add_rows_kernel(float* __restrict__ y, int ldy, int nq, int cv, const float* __restrict__ z, int ns,
+                       const void* __restrict__ inds, int h) {
+    pdl_enter();
+    const size_t total = (size_t)nq * cv;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(t / cv), c = (int)(t % cv) * 4;
+        const int j = load_idx<IdxT>(inds, (size_t)r * h);
+        if (j < 0 || j >= ns) continue;
+        float4 a = *(const float4*)(y + (size_t)r * ldy + c);
+        const float4 b = __ldg((const float4*)(z + (size_t)j * (cv * 4) + c));
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        *(float4*)(y + (size_t)r * ldy + c) = a;
+    }
+}
+
 bool fast_ok(int cin, int num_kp, int influence, int aggregation, int ld) {
     return influence == 1 && aggregation == 0 && num_kp <= KF && (cin == 32 || cin == 64 || cin % 128 == 0) &&
            (ld % 4 == 0);
@@ -1079,6 +1098,23 @@ int mvk_upsample_concat_split(const float* x_coarse, int ns, int c1, const void*
         launch_pdl(upcat_split_kernel<int>, grid, dim3(256), 0, (cudaStream_t)stream, 1, x_coarse, ns, c1,
                    (const int*)inds, h, skip, lds, c2, nq, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldh);
     MVK_LAUNCHED("upcat_split_kernel");
+    return MVK_OK;
+}
+
+int mvk_gather_add_rows(float* y, int ldy, int nq, int c, const float* z, int ns, const void* inds, int idx_is_i64, int h,
+                        mvk_stream_t stream) {
+    if (!y || !z || !inds || nq < 0 || ns < 0 || c < 4 || (c % 4) != 0 || ldy < c || (ldy % 4) != 0 || h < 1 ||
+        ((((size_t)y) | ((size_t)z)) & 15) != 0)
+        return MVK_ERR_INVALID_ARG;
+    if (nq == 0) return MVK_OK;
+    const size_t nv = (size_t)nq * (c / 4);
+    size_t nb = (nv + 255) / 256, mb = (size_t)num_sms() * 16;
+    const dim3 grid((unsigned)(nb < mb ? nb : mb));
+    if (idx_is_i64)
+        launch_pdl(gather_add_rows_kernel<long long>, grid, dim3(256), 0, (cudaStream_t)stream, 1, y, ldy, nq, c / 4, z, ns, inds, h);
+    else
+        launch_pdl(gather_add_rows_kernel<int>, grid, dim3(256), 0, (cudaStream_t)stream, 1, y, ldy, nq, c / 4, z, ns, inds, h);
+    MVK_LAUNCHED("gather_add_rows_kernel");
     return MVK_OK;
 }
 

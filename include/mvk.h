@@ -280,6 +280,11 @@ int mvk_softmax_xent_bwd(const float* logits, int ld, const long long* labels, i
  * bf16 hi/lo operand [nq, ldh] of the following unary block's Linear (the fp32 concatenation is never
  * materialised).  inds [nq, h]: only column 0 is used; index ns (shadow) gathers zeros.  c1, c2, lds, ldh
  * multiples of 4. */
+/* y[r, 0:c] += z[inds[r, 0], 0:c] for r < nq (y row pitch ldy; rows whose first index is outside [0, ns) are left
+ * alone).  The gathered half of the decoder step contracted at the coarse level:
+ * cat([closest_pool(x, up), skip], 1) W^T = closest_pool(x W_up^T, up) + skip W_skip^T  (architectures.py:300-306). */
+int mvk_gather_add_rows(float* y, int ldy, int nq, int c, const float* z, int ns, const void* inds, int idx_is_i64,
+                        int h, mvk_stream_t stream);
 int mvk_upsample_concat_split(const float* x_coarse, int ns, int c1, const void* inds, int idx_is_i64, int nq, int h,
                               const float* skip, int lds, int c2, void* hi_bf16, void* lo_bf16, int ldh,
                               mvk_stream_t stream);

@@ -230,19 +230,32 @@ def test_fused_decoder_step_matches_unfused(mvk):
     xc0 = torch.randn(ns, c1, device=dev)
     sk0 = torch.randn(nq, c2, device=dev)
     gz = torch.randn(nq, cout, device=dev)
+    from mvkpconv_b200 import blocks as blocks_mod
     res = {}
-    for mode in ("fused", "plain"):
+    # "split": upsampled half contracted at the coarse level + gathered (_UpAddLinearBNAct, the default);
+    # "cat": concatenated bf16 operand (_UpCatLinearBNAct); "plain": the reference's op sequence
+    for mode in ("split", "cat", "plain"):
         blk.zero_grad(set_to_none=True)
         xc, sk = xc0.clone().requires_grad_(True), sk0.clone().requires_grad_(True)
-        if mode == "fused":
-            z = blk.forward_upsampled(xc, up, sk)
-        else:
+        if mode == "plain":
             z = blk(torch.cat([mvk.closest_pool(xc, up), sk], dim=1))
+        else:
+            blocks_mod._DECODER_SPLIT = mode == "split"
+            try:
+                z = blk.forward_upsampled(xc, up, sk)
+            finally:
+                blocks_mod._DECODER_SPLIT = True
+            assert type(z.grad_fn).__name__.startswith("_UpAdd" if mode == "split" else "_UpCat")
         (z * gz).sum().backward()
         res[mode] = [z.detach(), xc.grad, sk.grad, blk.mlp.weight.grad.clone(), blk.batch_norm.batch_norm.weight.grad.clone(),
                      blk.batch_norm.batch_norm.bias.grad.clone()]
-    for a, b in zip(res["fused"], res["plain"]):
-        assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-7
+    for mode in ("split", "cat"):
+        for a, b in zip(res[mode], res["plain"]):
+            assert float((a - b).abs().max()) <= 2e-5 * float(b.abs().max()) + 1e-7, mode
+    # inference (no graph) and an empty coarse level
+    with torch.no_grad():
+        zi = blk.forward_upsampled(xc0, up, sk0)
+    assert float((zi - res["plain"][0]).abs().max()) <= 2e-5 * float(res["plain"][0].abs().max())
     blk.contraction = "fp32"   # falls back to the unfused sequence
     z = blk.forward_upsampled(xc0, up, sk0)
     assert float((z.detach() - res["plain"][0]).abs().max()) <= 1e-4 * float(res["plain"][0].abs().max())
