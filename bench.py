@@ -1032,7 +1032,8 @@ def cpu_reference(steps, warmup, seed=0, n_spheres=SPHERES_PER_GPU):
             "kind_detail": ("pyramid (radius neighbours, grid subsampling) = the UNMODIFIED reference C++ compiled from "
                             "/root/reference (oracle/_ref/libref.so); " if have_ref else "pyramid = the plain-C restatement; ")
                            + "network = torch-CPU restatement of the reference graph (oracle.modules.KPConvOracle + torch "
-                             "Linear / BatchNorm1d / LeakyReLU), not the reference's own Python files (absent on the GPU box)",
+                             "Linear / BatchNorm1d / LeakyReLU; reproduces the reference's own KPFCNN class on a golden "
+                             "batch, tests/test_fusion_golden.py), not the reference's Python files (absent on the GPU box)",
             "sample": f"the whole batch: {n_spheres} of {SPHERES_PER_GPU} spheres ({len(pts)} points), {steps} step(s) after "
                       f"{warmup} warm-up; pyramid 1 thread (like a reference DataLoader worker), network {cores} threads",
             "ms_per_step": round(1e3 * dt / steps, 1), "ms_pyramid": round(1e3 * t_pyr / steps, 1),

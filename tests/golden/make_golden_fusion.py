@@ -157,5 +157,54 @@ def make(which):
     print(which, out.shape, float(loss.detach()), len(sd), "tensors,", round(os.path.getsize(path) / 1e6, 2), "MB")
 
 
+def make_baseline():
+    """The KPFCNN of the baseline training script (models/architectures.py:189-352, rigid + deformable blocks) run by
+    the reference's own class: forward, its loss incl. the deformable regulariser (p2p_fitting_regularizer), backward."""
+    from types import SimpleNamespace
+    from oracle import geom
+    from mvkpconv_b200 import pyramid
+    from test_gpu_network import cloud
+    import_reference("early")  # sets up the stubs, sys.path and cwd
+    import importlib
+    arch = importlib.import_module("models.architectures")
+    rng = np.random.default_rng(5)
+    pts = np.concatenate([cloud(rng, 1100), cloud(rng, 900)], 0)
+    lens = np.array([1100, 900], np.int32)
+    cfg = pyramid.baseline_config(architecture=list(ARCH_DEFORM), first_subsampling_dl=0.03, first_features_dim=16, num_classes=6,
+                                  in_features_dim=2, deform_radius=4.0)
+    cfg.class_w = []
+    cfg.deform_lr_factor = 0.1
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = arch.KPFCNN(cfg, np.arange(6), [])
+    net.train()
+    gops = SimpleNamespace(batch_neighbors=geom.ref_batch_neighbors if geom.have_ref() else geom.batch_neighbors,
+                           batch_grid_subsampling=lambda p, l, sampleDl=0.1, random_grid_orient=True:
+                           (geom.ref_grid_subsample_batch if geom.have_ref() else geom.grid_subsample_batch)(p, l, sampleDl=sampleDl))
+    pyr = pyramid.build_pyramid(pts, lens, cfg, ops=gops, random_grid_orient=False)
+    feats = np.concatenate([np.ones((len(pts), 1), np.float32), pts[:, 2:3]], 1)
+    labels = rng.integers(0, 6, len(pts)).astype(np.int64)
+    as_t = lambda lst, dt: [torch.from_numpy(np.ascontiguousarray(a)).to(dt) for a in lst]
+    batch = SimpleNamespace(points=as_t(pyr.points, torch.float32), neighbors=as_t(pyr.neighbors, torch.int64),
+                            pools=as_t(pyr.pools, torch.int64), upsamples=as_t(pyr.upsamples, torch.int64),
+                            lengths=pyr.lengths, features=torch.from_numpy(feats))
+    out = net(batch, cfg)
+    loss = net.loss(out, torch.from_numpy(labels))
+    loss.backward()
+    fix = dict(lens=lens, points=pts, features=feats, labels=labels, logits=out.detach().numpy(),
+               loss=np.float32(float(loss.detach())), output_loss=np.float32(float(net.output_loss.detach())),
+               reg_loss=np.float32(float(net.reg_loss.detach())),
+               versions=np.array(f"torch {torch.__version__}; numpy {np.__version__}"))
+    for k, v in net.state_dict().items():
+        fix["sd/" + k] = v.detach().numpy()
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            fix["grad/" + k] = p.grad.numpy().astype(np.float32)
+    path = os.path.join(OUT, "kpfcnn_baseline.npz")
+    np.savez_compressed(path, **fix)
+    print("baseline", out.shape, float(loss.detach()), float(net.reg_loss.detach()), round(os.path.getsize(path) / 1e6, 2), "MB")
+
+
 if __name__ == "__main__":
-    make(sys.argv[1] if len(sys.argv) > 1 else "early")
+    which = sys.argv[1] if len(sys.argv) > 1 else "early"
+    make_baseline() if which == "baseline" else make(which)

@@ -154,3 +154,86 @@ def test_fusion_product_vs_reference_golden(mvk, which, contraction):
     assert l2 < (1e-4 if strict else 2e-2)
     if strict:
         assert worst[1] < 1e-3, worst
+
+
+# -------------------------------------------------------------------------------------------------
+# The baseline KPFCNN (BASELINE configs[1] architecture family) against the reference's own class
+# (models/architectures.py:189-352 incl. p2p_fitting_regularizer :21-54), golden = tests/golden/kpfcnn_baseline.npz
+# -------------------------------------------------------------------------------------------------
+def _baseline():
+    from mvkpconv_b200 import pyramid
+    z = np.load(os.path.join(GOLDEN, "kpfcnn_baseline.npz"), allow_pickle=False)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    grads = {k[5:]: z[k] for k in z.files if k.startswith("grad/")}
+    cfg = pyramid.baseline_config(architecture=list(ARCHS["middle"]), first_subsampling_dl=0.03, first_features_dim=16,
+                                  num_classes=6, in_features_dim=2, deform_radius=4.0)
+    return z, sd, grads, cfg
+
+
+def test_kpfcnn_oracle_graph_reproduces_reference_golden():
+    """harness.KPFCNN composed from the oracle operators == the reference's KPFCNN (same state dict, strict): logits,
+    loss (cross entropy + deformable fitting / repulsion regulariser) and every parameter gradient.  This is the
+    graph bench.py's CPU arm runs, so the arm's network half is pinned on the reference as well."""
+    from mvkpconv_b200 import harness, pyramid
+    z, sd, grads, cfg = _baseline()
+    gops = SimpleNamespace(batch_neighbors=geom.batch_neighbors,
+                           batch_grid_subsampling=lambda p, l, sampleDl=0.1, random_grid_orient=True:
+                           geom.grid_subsample_batch(p, l, sampleDl=sampleDl))
+    mops = SimpleNamespace(KPConv=modules.KPConvOracle, max_pool=modules.max_pool, closest_pool=modules.closest_pool)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = harness.KPFCNN(cfg, ops=mops)
+    net.load_state_dict(sd, strict=True)
+    net.train()
+    pyr = pyramid.build_pyramid(z["points"], z["lens"], cfg, ops=gops, random_grid_orient=False)
+    as_t = lambda lst, dt: [torch.from_numpy(np.ascontiguousarray(a)).to(dt) for a in lst]
+    batch = SimpleNamespace(points=as_t(pyr.points, torch.float32), neighbors=as_t(pyr.neighbors, torch.int64),
+                            pools=as_t(pyr.pools, torch.int64), upsamples=as_t(pyr.upsamples, torch.int64),
+                            lengths=pyr.lengths, features=torch.from_numpy(z["features"]))
+    out = net(batch)
+    loss = net.loss(out, torch.from_numpy(z["labels"]))
+    loss.backward()
+    assert rel_err(out, z["logits"]) < 1e-5
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-5 * abs(float(z["loss"]))
+    got = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    assert set(got) == set(grads), set(got) ^ set(grads)
+    for k, g in grads.items():
+        if np.abs(g).max() > 1e-7:
+            assert rel_err(got[k], g) < 1e-4, k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("contraction", ["fp32", "bf16x3"])
+def test_kpfcnn_product_vs_reference_golden(mvk, contraction):
+    from mvkpconv_b200 import harness, pyramid
+    z, sd, grads, cfg = _baseline()
+    dev = torch.device("cuda")
+    np.random.seed(0)
+    torch.manual_seed(0)
+    net = harness.KPFCNN(cfg).to(dev)
+    net.load_state_dict(sd, strict=True)
+    for m in net.modules():
+        if hasattr(m, "contraction"):
+            m.contraction = contraction
+    net.train()
+    pyr = pyramid.build_pyramid(torch.from_numpy(z["points"]).to(dev), torch.from_numpy(z["lens"]).to(dev), cfg,
+                                random_grid_orient=False)
+    batch = SimpleNamespace(points=pyr.points, neighbors=pyr.neighbors, pools=pyr.pools, upsamples=pyr.upsamples,
+                            lengths=pyr.lengths, features=torch.from_numpy(z["features"]).to(dev))
+    out = net(batch)
+    loss = net.loss(out, torch.from_numpy(z["labels"]).to(dev))
+    loss.backward()
+    strict = contraction == "fp32"
+    e_out = rel_err(out, z["logits"])
+    e_loss = abs(float(loss.detach()) - float(z["loss"])) / abs(float(z["loss"]))
+    got = {k: p.grad for k, p in net.named_parameters() if p.grad is not None}
+    num = den = 0.0
+    for k, g in grads.items():
+        d = got[k].detach().double().cpu().numpy() - g.astype(np.float64)
+        num += float((d * d).sum())
+        den += float((g.astype(np.float64) ** 2).sum())
+    l2 = (num / den) ** 0.5
+    print(f"KPFCNN [{contraction}] vs reference golden: logits {e_out:.2e} loss {e_loss:.2e} grads L2 {l2:.2e}")
+    assert e_out < (1e-4 if strict else 2e-3)
+    assert e_loss < (1e-4 if strict else 2e-3)
+    assert l2 < (1e-4 if strict else 2e-2)
