@@ -30,6 +30,7 @@ struct KpArgs {
     int nq, ns, h, cin, K, ld;
     float extent;
     int influence, aggregation;
+    int width;  // columns of a row this call owns (K*cin values + zero padding up to width); == ld unless the row is shared
 };
 
 template <typename IdxT>
@@ -196,7 +197,7 @@ kp_weighted_fwd(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict
                 }
             }
         }
-        for (int c = kd + lane; c < a.ld; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
+        for (int c = kd + lane; c < a.width; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
         __syncwarp();
     }
 }
@@ -635,7 +636,7 @@ kp_fwd_fast(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ o
                 if (k < a.K) store4(out_f32, out_hi, out_lo, row + (unsigned int)(k * cin + cb + lg * 4), acc);
             }
         }
-        for (int c = kd + lane; c < a.ld; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
+        for (int c = kd + lane; c < a.width; c += 32) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
         __syncwarp();
     }
 }
@@ -677,7 +678,7 @@ kp_fwd_tiny(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ o
         }
     }
     const size_t row = (size_t)i * a.ld;
-    if (out_hi && (a.ld % 8) == 0 && a.ld <= KF * 4) {
+    if (out_hi && a.width == a.ld && (a.ld % 8) == 0 && a.ld <= KF * 4) {
         // the whole bf16 row (zero padding included) as ld/8 + ld/8 128-bit stores
 #pragma unroll
         for (int v8 = 0; v8 < 8; v8++) {
@@ -708,7 +709,7 @@ kp_fwd_tiny(KpArgs a, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ o
 #pragma unroll
         for (int c = 0; c < CIN; c++)
             if (k < a.K) store_out(out_f32, out_hi, out_lo, row + k * CIN + c, acc[k][c]);
-    for (int c = a.K * CIN; c < a.ld; c++) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
+    for (int c = a.K * CIN; c < a.width; c++) store_out(out_f32, out_hi, out_lo, row + c, 0.f);
 }
 
 // ---- backward w.r.t. x, cin in {32, 64, 128 m} ---------------------------------------------------------
@@ -870,17 +871,30 @@ using namespace mvk;
 
 extern "C" {
 
+int mvk_kpconv_weighted_part(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                             int idx_is_i64, int h, const float* x, int cin, const float* kernel_points, int num_kp,
+                             float kp_extent, int influence, int aggregation, int ld, int width, float* out_f32,
+                             void* out_hi, void* out_lo, mvk_stream_t stream);
+
 int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
                         int idx_is_i64, int h, const float* x, int cin, const float* kernel_points,
                         int num_kp, float kp_extent, int influence, int aggregation, int ld,
                         float* out_f32, void* out_hi, void* out_lo, mvk_stream_t stream) {
-    if (nq < 0 || ns < 0 || h < 1 || cin < 1 || num_kp < 1 || num_kp > KP_MAX || ld < num_kp * cin ||
-        (!out_f32 && !(out_hi && out_lo)) || !(kp_extent > 0.f))
+    return mvk_kpconv_weighted_part(q_pts, nq, s_pts, ns, neighb_inds, idx_is_i64, h, x, cin, kernel_points, num_kp,
+                                    kp_extent, influence, aggregation, ld, ld, out_f32, out_hi, out_lo, stream);
+}
+
+int mvk_kpconv_weighted_part(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                             int idx_is_i64, int h, const float* x, int cin, const float* kernel_points, int num_kp,
+                             float kp_extent, int influence, int aggregation, int ld, int width, float* out_f32,
+                             void* out_hi, void* out_lo, mvk_stream_t stream) {
+    if (nq < 0 || ns < 0 || h < 1 || cin < 1 || num_kp < 1 || num_kp > KP_MAX || ld < num_kp * cin || width < num_kp * cin ||
+        width > ld || (!out_f32 && !(out_hi && out_lo)) || !(kp_extent > 0.f))
         return MVK_ERR_INVALID_ARG;
     if (influence < 0 || influence > 2 || aggregation < 0 || aggregation > 1) return MVK_ERR_UNSUPPORTED;
     if (nq == 0) return MVK_OK;
     KpArgs a{q_pts, s_pts, neighb_inds, x, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
-             influence, aggregation};
+             influence, aggregation, width};
     cudaStream_t st = (cudaStream_t)stream;
     if (tiny_ok(cin, num_kp, influence, aggregation)) {
         const int threads = 128, blocks_t = (nq + threads - 1) / threads;
@@ -981,7 +995,7 @@ int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int 
     if (influence < 0 || influence > 2 || aggregation < 0 || aggregation > 1) return MVK_ERR_UNSUPPORTED;
     if (nq == 0) return MVK_OK;
     KpArgs a{q_pts, s_pts, neighb_inds, nullptr, kernel_points, nq, ns, h, cin, num_kp, ld, kp_extent,
-             influence, aggregation};
+             influence, aggregation, ld};
     if (fast_ok(cin, num_kp, influence, aggregation, ld) && h <= 64 && (size_t)(ns + 1) * cin * 4 < 0xffffffffull &&
         (size_t)ld < 0x7fffffffull) {
         const int G = fast_g(cin);

@@ -62,6 +62,29 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+_SPLIT_PERM = {}
+
+
+def _channel_split(cin, K, h, influence, aggregation, device):
+    """(c_rest, c_main, perm) when cin = c_rest + c_main with 1 <= c_rest <= 4 leading channels and a fast-path width
+    c_main behind them (66 = 2 + 64, 65 = 1 + 64, 68 = 4 + 64, ...), else None.  perm[j] = row of W [K*cin, cout] that
+    column j of the K-concatenated operand [A_main (k, c_main) | A_rest (k, c_rest)] multiplies."""
+    c_rest = cin % 32
+    c_main = cin - c_rest
+    if not (1 <= c_rest <= 4 and (c_main in (32, 64) or (c_main > 0 and c_main % 128 == 0))):
+        return None
+    if influence != 1 or aggregation != 0 or K > 16 or h > 64:
+        return None
+    key = (cin, K, device.index)
+    perm = _SPLIT_PERM.get(key)
+    if perm is None:
+        k = torch.arange(K).unsqueeze(1)
+        main = (k * cin + c_rest + torch.arange(c_main).unsqueeze(0)).reshape(-1)
+        rest = (k * cin + torch.arange(c_rest).unsqueeze(0)).reshape(-1)
+        perm = _SPLIT_PERM[key] = torch.cat([main, rest]).to(device)
+    return c_rest, c_main, perm
+
+
 def _carve(device, *sizes):
     """ONE device allocation carved into 256-byte aligned raw sub-buffers -> (keep-alive tensor, [ptr | None])."""
     offs, total = [], 0
@@ -112,11 +135,34 @@ class _KPConvFunction(torch.autograd.Function):
                 need_a = bool(ctx.needs_input_grad[4])  # (all False under torch.no_grad(): inference keeps nothing)
                 fused = (FUSED_FORWARD and terms == 3 and nq > 0 and
                          L.mvk_kpconv_fused_supported(cin, cout, K, h, influence, aggregation) == 1)
+                split = None if fused else _channel_split(cin, K, h, influence, aggregation, dev)
                 if fused:
                     keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld if need_a else 0, 2 * nq * ld if need_a else 0)
                     check(L.mvk_kpconv_fused(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(), cin,
                                              kp.data_ptr(), K, float(kp_extent), cout, w_hi, w_lo, npad, out.data_ptr(),
                                              a_hi, a_lo, ld, st))
+                elif split is not None:
+                    # Cin = c_rest + c_main (e.g. 66 = 2 + 64, the first layer of the early-fusion net): the wide part
+                    # runs the fast stage-A kernel, the narrow part the small-Cin kernel, both into ONE K-concatenated
+                    # operand [A_main | A_rest | 0]; the weight rows are permuted to match (KPConv is linear in x)
+                    c_rest, c_main, perm = split
+                    keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld)
+                    x_main = xf[:, c_rest:].contiguous()
+                    x_rest = xf[:, :c_rest].contiguous()
+                    km = K * c_main
+                    check(L.mvk_kpconv_weighted_part(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h,
+                                                     x_main.data_ptr(), c_main, kp.data_ptr(), K, float(kp_extent), influence,
+                                                     aggregation, ld, km, None, a_hi, a_lo, st))
+                    check(L.mvk_kpconv_weighted_part(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h,
+                                                     x_rest.data_ptr(), c_rest, kp.data_ptr(), K, float(kp_extent), influence,
+                                                     aggregation, ld, ld - km, None, a_hi + 2 * km, a_lo + 2 * km, st))
+                    w_perm = w.reshape(kd, cout).index_select(0, perm)
+                    wkeep = torch.empty(2 * ((2 * ld * npad + 255) & ~255), dtype=torch.uint8, device=dev)
+                    w_hi, w_lo = wkeep.data_ptr(), wkeep.data_ptr() + ((2 * ld * npad + 255) & ~255)
+                    check(L.mvk_split_bf16(w_perm.data_ptr(), kd, cout, cout, w_hi, w_lo, ld, npad, st))
+                    if nq > 0:
+                        check(L.mvk_gemm_bf16x3(a_hi, a_lo, 0, ld, w_hi, w_lo, 1, npad, nq, npad, ld, out.data_ptr(), cout,
+                                                cout, terms, 0, st))
                 else:
                     keep, (a_hi, a_lo) = _carve(dev, 2 * nq * ld, 2 * nq * ld)
                     check(L.mvk_kpconv_weighted(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, xf.data_ptr(),
@@ -129,6 +175,7 @@ class _KPConvFunction(torch.autograd.Function):
         ctx.save_for_backward(q, s, inds, kp, w, keep)  # autograd's version check on w also guards its bf16 pair
         ctx.cfg = (nq, ns, h, K, cin, cout, float(kp_extent), influence, aggregation, contraction, is64, ld, npad, ptrs)
         ctx.wkeep = None if fp32 else wkeep
+        ctx.split = None if fp32 else split
         return out
 
     @staticmethod
@@ -180,12 +227,29 @@ class _KPConvFunction(torch.autograd.Function):
                     # dA = dOut W^T : A = dOut [nq, npad] K-major, B = W [ld, npad] K-major
                     check(L.mvk_gemm_bf16x3(go_hi, go_lo, 0, npad, w_hi, w_lo, 0, npad, nq, ld, npad, dA, ld, ld, terms,
                                             0, st))
-            if need_x:
+            split = getattr(ctx, "split", None)
+            if need_x and split is not None:
+                c_rest, c_main, perm = split
+                km = K * c_main
+                gx_main = torch.zeros((ns, c_main), dtype=torch.float32, device=dev)
+                gx_rest = torch.zeros((ns, c_rest), dtype=torch.float32, device=dev)
+                if nq > 0:
+                    check(L.mvk_kpconv_weighted_bwd(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, c_main,
+                                                    kp.data_ptr(), K, extent, influence, aggregation, dA, ld,
+                                                    gx_main.data_ptr(), st))
+                    check(L.mvk_kpconv_weighted_bwd(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, c_rest,
+                                                    kp.data_ptr(), K, extent, influence, aggregation, dA + 4 * km, ld,
+                                                    gx_rest.data_ptr(), st))
+                gx = torch.cat([gx_rest, gx_main], dim=1)
+            elif need_x:
                 gx = torch.zeros((ns, cin), dtype=torch.float32, device=dev)
                 if nq > 0:
                     check(L.mvk_kpconv_weighted_bwd(q.data_ptr(), nq, s.data_ptr(), ns, inds.data_ptr(), is64, h, cin,
                                                     kp.data_ptr(), K, extent, influence, aggregation, dA, ld, gx.data_ptr(),
                                                     st))
+            if gw is not None and split is not None:
+                # rows of dW are in the operand's order [main | rest]: back to the parameter's (k, c) order
+                gw = torch.zeros_like(gw).view(kd, cout).index_copy_(0, split[2], gw.view(kd, cout)).view(K, cin, cout)
         return None, None, None, gx, gw, None, None, None, None, None
 
 

@@ -146,6 +146,13 @@ int mvk_kpconv_weighted(const float* q_pts, int nq, const float* s_pts, int ns, 
                         float* out_f32, void* out_hi_bf16, void* out_lo_bf16, mvk_stream_t stream);
 /* Backward of stage A w.r.t. x:  grad_x[j, c] += sum_k w_ihk * grad_weighted[i, k*cin + c]
  * (grad_x [ns, cin] must be zero-initialised by the caller; fp32 atomics). */
+/* mvk_kpconv_weighted for a row SHARED by several calls (K-concatenated operand of a layer whose input channels are
+ * handled in parts, e.g. 66 = 64 on the fast path + 2 on the small-Cin path): this call writes columns [0, num_kp*cin) of
+ * the rows starting at out_* (row pitch ld) and zero-fills up to `width`; nothing beyond `width` is touched. */
+int mvk_kpconv_weighted_part(const float* q_pts, int nq, const float* s_pts, int ns, const void* neighb_inds,
+                             int idx_is_i64, int h, const float* x, int cin, const float* kernel_points, int num_kp,
+                             float kp_extent, int influence, int aggregation, int ld, int width, float* out_f32,
+                             void* out_hi, void* out_lo, mvk_stream_t stream);
 int mvk_kpconv_weighted_bwd(const float* q_pts, int nq, const float* s_pts, int ns,
                             const void* neighb_inds, int idx_is_i64, int h, int cin,
                             const float* kernel_points, int num_kp, float kp_extent, int influence,

@@ -60,9 +60,12 @@ def test_kpconv_int32_indices_equal_int64(mvk):
 
 
 @pytest.mark.parametrize("cin,cout,n,strided", [(32, 32, 6000, False), (64, 64, 5000, True), (128, 128, 1500, False),
-                                                (256, 256, 700, False), (4, 64, 4000, False), (66, 64, 3000, False)])
+                                                (256, 256, 700, False), (4, 64, 4000, False), (66, 64, 3000, False),
+                                                (65, 64, 2500, True), (36, 32, 2000, False), (70, 64, 1500, False)])
 def test_kpconv_vs_oracle_seeded(mvk, cin, cout, n, strided):
-    """Layer shapes of the baseline / fusion nets on real neighbourhoods."""
+    """Layer shapes of the baseline / fusion nets on real neighbourhoods.  66 / 65 / 36 input channels
+    take the channel-split path (2 + 64, 1 + 64, 4 + 32: fast stage A + small-Cin stage A into one K-concatenated
+    operand, weight rows permuted), 70 the generic kernels."""
     rng = np.random.default_rng(cin * 1000 + cout)
     s_pts = bumpy_cloud(rng, n)
     lens = np.array([n // 2, n - n // 2], np.int32)
