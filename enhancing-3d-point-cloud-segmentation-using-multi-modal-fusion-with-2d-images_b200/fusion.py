@@ -97,6 +97,33 @@ class UNetResNet34(nn.Module):
         return {'seg_logit': self.logit(x), 'feature': x}
 
 
+def fold_batch_norm(net):
+    """Inference copy of a frozen 2D network with every (Conv2d | ConvTranspose2d) -> BatchNorm2d pair folded into the
+    convolution (eval-mode batch norm is an affine map per channel): same function up to rounding, ~44 fewer
+    kernels per UNet-ResNet34 forward.  The original module (and its state dict / parameter names) is left untouched."""
+    import copy
+    from torch.nn.utils.fusion import fuse_conv_bn_eval
+    m = copy.deepcopy(net).eval()
+
+    def fold_children(parent):
+        names = list(parent._modules.keys())
+        for a, b in zip(names, names[1:]):
+            conv, bn = parent._modules[a], parent._modules[b]
+            if isinstance(conv, (nn.Conv2d, nn.ConvTranspose2d)) and isinstance(bn, nn.BatchNorm2d):
+                parent._modules[a] = fuse_conv_bn_eval(conv, bn, transpose=isinstance(conv, nn.ConvTranspose2d))
+                parent._modules[b] = nn.Identity()
+        for child in parent._modules.values():
+            if child is not None:
+                fold_children(child)
+
+    fold_children(m)
+    # torchvision BasicBlock: conv1 -> bn1, conv2 -> bn2 are adjacent children as well (handled above); the UNet's stem
+    # is encoder0 -> bn (adjacent in definition order)
+    for p in m.parameters():
+        p.requires_grad = False
+    return m
+
+
 # -------------------------------------------------------------------------------------------------
 def prepare_lifting(cam_matrices, depths, poses, feat_aggre_points, lengths, k=3, kinv=None):
     """The numeric half of ``get_rgbd_data`` (ScanNet_sphere_color.py:409-452) for a whole batch on the GPU:
@@ -127,13 +154,14 @@ class FusionKPFCNN(nn.Module):
     """
 
     def __init__(self, config, fusion="early", net_2d=None, num_classes=None, ops=None, bottleneck="mean",
-                 precision_2d="fp32"):
+                 precision_2d="fp32", fold_bn=True):
         super().__init__()
         if fusion not in ("early", "middle", "late"):
             raise ValueError("fusion must be 'early', 'middle' or 'late'")
         if bottleneck not in ("cat", "mean"):
             raise ValueError("bottleneck must be 'cat' or 'mean'")
         self.fusion, self.bottleneck, self.precision_2d = fusion, bottleneck, precision_2d
+        self.fold_bn, self._folded = fold_bn, None
         self._product_ops = ops is None
         ops = ops or _h.product_ops()
         self.ops = ops
@@ -202,15 +230,28 @@ class FusionKPFCNN(nn.Module):
             m.train(False)
 
     # ---- 2D network + lifting ---------------------------------------------------------------------
+    def _net2d_for_inference(self):
+        """The frozen 2D network, with its batch norms folded into the convolutions when it runs in eval mode on the
+        GPU (product path); re-folded whenever a parameter or buffer of the original changed (checkpoint load)."""
+        net = self.net_2d
+        if not (self.fold_bn and self._product_ops) or any(m.training for m in net.modules() if isinstance(m, nn.BatchNorm2d)):
+            return net
+        key = tuple((t.data_ptr(), t._version) for t in list(net.parameters()) + list(net.buffers()))
+        if self._folded is None or self._folded[0] != key:
+            object.__setattr__(self, "_folded", (key, fold_batch_norm(net)))  # not a registered submodule
+        return self._folded[1]
+
     def features_2d(self, images):
         b, nv = images.shape[:2]
         x = images.reshape((b * nv,) + tuple(images.shape[2:]))
         with torch.no_grad():
             if x.is_cuda:
+                net = self._net2d_for_inference()
                 x = x.contiguous(memory_format=torch.channels_last)
                 if self.precision_2d == "bf16":
                     with torch.autocast("cuda", dtype=torch.bfloat16):
-                        return self.net_2d({'image': x})['feature'].float()
+                        return net({'image': x})['feature'].float()
+                return net({'image': x})['feature']
             return self.net_2d({'image': x})['feature']
 
     def lift(self, batch):
