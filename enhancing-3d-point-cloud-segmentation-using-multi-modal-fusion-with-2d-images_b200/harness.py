@@ -268,12 +268,16 @@ class OverlappedGradientAverager:
     most of its time afterwards in the shallow, point-heavy levels.  A post-accumulate hook on the LAST
     parameter of that early group starts its all-reduce asynchronously (NCCL's own stream), so the transfer
     hides behind the rest of backward; ``finish()`` (call it after ``loss.backward()``) reduces whatever is
-    left, waits, and divides by the world size.  No per-parameter hooks, no buckets, no copies.
+    left, waits, and divides by the world size.  No buckets, no copies.  A gradient counts as complete only once
+    its own post-accumulate hook has run in THIS backward pass, so gradients kept across steps
+    (``zero_grad(set_to_none=False)``, gradient accumulation) and the trigger block's parameters that accumulate
+    after the trigger are left to ``finish()`` instead of being sent while autograd still writes them.
 
     STATUS: correct (tests/test_distributed_cpu.py) but NOT the default of bench.py: on 2 B200s the concurrent
-    NCCL kernel slowed the step from 14.0 to 38.8 ms (round 1, one measurement, not yet analysed -- the
-    persistent contraction kernels and the collective compete for the same SMs); the grouped all-reduce
-    after backward stays the default.
+    NCCL kernel slowed the step from 14.0 to 38.8 ms (round 1: the persistent contraction CTAs hold 227 KB of
+    shared memory per SM, so the collective's CTAs and they cannot share an SM and each waits for the other);
+    the default is one flat all-reduce between the two captured graphs of ``GraphedTrainStep``.  One
+    ``backward()`` per ``finish()``.
 
         avg = OverlappedGradientAverager(net, split_level=3)     # once
         loss.backward(); avg.finish()                            # every step
@@ -296,8 +300,9 @@ class OverlappedGradientAverager:
         params = [p for p in net.parameters() if p.requires_grad]
         self.early = [p for p in params if id(p) not in late_ids]
         self.params = params
-        self._works, self._sent = [], set()
-        self._hook = trigger.register_post_accumulate_grad_hook(self._fire) if trigger is not None else None
+        self._works, self._sent, self._done = [], set(), set()
+        self._trigger = trigger
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.early] if trigger is not None else []
 
     def _reduce(self, tensors, async_op):
         dist = self.dist
@@ -315,10 +320,15 @@ class OverlappedGradientAverager:
                 if async_op:
                     self._works.append(w)
 
-    def _fire(self, _param):
+    def _on_grad(self, param):
+        self._done.add(id(param))
+        if param is self._trigger:
+            self._fire()
+
+    def _fire(self):
         if self._sent:  # a second backward before finish(): leave everything to finish()
             return
-        ready = [p for p in self.early if p.grad is not None]
+        ready = [p for p in self.early if id(p) in self._done and p.grad is not None]
         self._sent = {id(p) for p in ready}
         self._reduce([p.grad for p in ready], async_op=True)
 
@@ -327,7 +337,7 @@ class OverlappedGradientAverager:
         self._reduce(rest, async_op=False)
         for w in self._works:
             w.wait()
-        self._works, self._sent = [], set()
+        self._works, self._sent, self._done = [], set(), set()
         grads = [p.grad for p in self.params if p.grad is not None]
         if grads:
             torch._foreach_div_(grads, float(self.world))

@@ -87,11 +87,18 @@ def _worker(rank, world, port, out_dir, mode="ddp"):
         from mvkpconv_b200 import harness
         avg = harness.OverlappedGradientAverager(net, split_level=1)
         assert 0 < len(avg.early) < len(avg.params)
+        keep = mode == "overlap_kept"  # gradients zeroed in place: a stale tensor is not a finished gradient
         for _ in range(2):  # the hook must re-arm for every step
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad(set_to_none=not keep)
             loss = net.loss(net(batch), batch.labels)
+            sent_at_fire = []
+            fire = avg._fire
+            avg._fire = lambda: (fire(), sent_at_fire.append((set(avg._sent), set(avg._done))))
             loss.backward()
+            avg._fire = fire
             assert avg._sent, "the early group was not sent from inside backward"
+            sent, done = sent_at_fire[0]
+            assert sent <= done, "a gradient went out before its accumulation finished"
             avg.finish()
     g = _grads(net)
     opt.step()
@@ -104,7 +111,7 @@ def _worker(rank, world, port, out_dir, mode="ddp"):
 import pytest
 
 
-@pytest.mark.parametrize("mode", ["ddp", "overlap"])
+@pytest.mark.parametrize("mode", ["ddp", "overlap", "overlap_kept"])
 def test_two_rank_sphere_sharded_step(tmp_path, mode):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path), mode), nprocs=world, join=True)
